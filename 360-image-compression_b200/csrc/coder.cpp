@@ -1,0 +1,261 @@
+// Host arithmetic coder: same bitstream as the reference's Coder / ArithmeticEncoder / ArithmeticDecoder /
+// BitOutputStream / BitInputStream (/root/reference/extension/coder.{h,cpp}, ArithmeticCoder.cpp:15-171,
+// BitIoStream.cpp:13-71): 32-bit state range coder, MSB-first bit order, terminator = a single `1` bit followed by
+// zero padding to a byte boundary, EOF reads as zero bits.
+//
+// Written from the arithmetic, not from the reference classes: the per-bit renormalisation loops
+// (ArithmeticCoder.cpp:56-68) are collapsed with count-leading-zeros into one multi-bit shift for the
+// "matching top bits" phase and one for the underflow phase, bits go through a 64-bit accumulator instead of an
+// iostream, and the power-of-two total (65536 for every table of this codec) turns the two divisions of the range
+// update into shifts.  tests/test_coder.py checks byte-identical streams against oracle/_ref/libref_coder.so
+// (the reference's own classes).
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/lic360_b200.h"
+
+namespace lic360 {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+constexpr uint64_t kMask = 0xFFFFFFFFull, kTop = 0x80000000ull, kSecond = 0x40000000ull;
+constexpr uint64_t kMinRange = (1ull << 30) + 2;  // ArithmeticCoder.cpp:20, also MAX_TOTAL (:21)
+
+struct BitWriter {
+    std::vector<uint8_t> bytes;
+    uint64_t acc = 0;  // pending bits, right-aligned
+    int nacc = 0;
+    void reset() { bytes.clear(); acc = 0; nacc = 0; }
+    inline void flush_bytes() {
+        while (nacc >= 8) {
+            nacc -= 8;
+            bytes.push_back((uint8_t)(acc >> nacc));
+        }
+        acc &= (1ull << nacc) - 1;
+    }
+    inline void put(uint32_t value, int n) {  // n <= 32
+        if (n == 0) return;
+        acc = (acc << n) | (value & ((n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1)));
+        nacc += n;
+        flush_bytes();
+    }
+    inline void put_run(int bit, uint64_t count) {
+        while (count > 0) {
+            int n = count > 32 ? 32 : (int)count;
+            put(bit ? 0xFFFFFFFFu : 0u, n);
+            count -= n;
+        }
+    }
+    void finish() {  // BitIoStream.cpp:68-71
+        if (nacc > 0) put(0, 8 - nacc);
+    }
+};
+
+struct BitReader {
+    const uint8_t* p = nullptr;
+    size_t len = 0, pos = 0;
+    uint64_t acc = 0;
+    int nacc = 0;
+    void reset(const uint8_t* data, size_t n) { p = data; len = n; pos = 0; acc = 0; nacc = 0; }
+    inline uint32_t get(int n) {  // n <= 32; past EOF reads zeros (ArithmeticCoder.cpp:131-136)
+        if (n == 0) return 0;
+        while (nacc < n) {
+            uint64_t b = pos < len ? p[pos] : 0;
+            pos++;
+            acc = (acc << 8) | b;
+            nacc += 8;
+        }
+        nacc -= n;
+        uint32_t v = (uint32_t)((acc >> nacc) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
+        acc &= (1ull << nacc) - 1;
+        return v;
+    }
+};
+
+}  // namespace
+
+struct lic360_coder {
+    std::string fname;
+    float fill = 3.5f;
+    uint64_t low = 0, high = kMask, code = 0, underflow = 0;
+    BitWriter bw;
+    BitReader br;
+    std::vector<uint8_t> input;
+    bool encoding = false, decoding = false, to_file = false;
+};
+
+namespace {
+
+// ArithmeticCoder.cpp:34-69 with both renormalisation loops collapsed.
+template <bool kDecode>
+inline int ac_update(lic360_coder* c, uint32_t sym_low, uint32_t sym_high, uint32_t total) {
+    const uint64_t range = c->high - c->low + 1;
+    if (sym_low == sym_high) { lic360::set_error("coder: symbol has zero frequency"); return LIC360_ERR_CODER; }
+    if (total > kMinRange) { lic360::set_error("coder: total too large"); return LIC360_ERR_CODER; }
+    uint64_t nl, nh;
+    if ((total & (total - 1)) == 0) {
+        const int sh = __builtin_ctz(total);
+        nl = c->low + (((uint64_t)sym_low * range) >> sh);
+        nh = c->low + (((uint64_t)sym_high * range) >> sh) - 1;
+    } else {
+        nl = c->low + (uint64_t)sym_low * range / total;
+        nh = c->low + (uint64_t)sym_high * range / total - 1;
+    }
+    uint32_t lo = (uint32_t)nl, hi = (uint32_t)nh;
+    const uint32_t diff = lo ^ hi;
+    if (diff == 0) { lic360::set_error("coder: low == high"); return LIC360_ERR_CODER; }
+    const int n = __builtin_clz(diff);  // leading bits shared by low and high: shifted out (":56-60")
+    if (n > 0) {
+        if (kDecode) {
+            c->code = ((c->code << n) & kMask) | c->br.get(n);
+        } else {
+            const int first = lo >> 31;
+            c->bw.put(first, 1);
+            if (c->underflow) { c->bw.put_run(first ^ 1, c->underflow); c->underflow = 0; }
+            if (n > 1) c->bw.put(lo >> (32 - n), n - 1);  // low n-1 bits of the top n bits of lo
+        }
+        lo <<= n;
+        hi = (hi << n) | ((1u << n) - 1);
+    }
+    // underflow phase (":62-68"): low = 01..., high = 10...  -> drop the second-highest bit k times
+    const uint32_t m = (lo & ~hi) << 1;
+    const int k = __builtin_clz(~m | 1u);  // consecutive ones from the top of m (k <= 31)
+    if (k > 0) {
+        if (kDecode) c->code = (c->code & kTop) | ((c->code << k) & (kMask >> 1)) | c->br.get(k);
+        else c->underflow += k;
+        lo = (lo << k) & 0x7FFFFFFFu;
+        hi = ((hi << k) & 0x7FFFFFFFu) | 0x80000000u | ((1u << k) - 1);
+    }
+    c->low = lo;
+    c->high = hi;
+    return LIC360_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+lic360_coder* lic360_coder_create(const char* fname, float fill_value) {
+    lic360_coder* c = new lic360_coder();
+    c->fname = fname ? fname : "";
+    c->fill = fill_value;
+    return c;
+}
+
+void lic360_coder_destroy(lic360_coder* c) { delete c; }
+
+int lic360_coder_reset_fname(lic360_coder* c, const char* fname) {
+    c->fname = fname ? fname : "";
+    return LIC360_OK;
+}
+
+int lic360_coder_start_encoder_mem(lic360_coder* c) {
+    c->low = 0; c->high = kMask; c->underflow = 0;
+    c->bw.reset();
+    c->encoding = true; c->decoding = false; c->to_file = false;
+    return LIC360_OK;
+}
+
+int lic360_coder_start_encoder(lic360_coder* c) {
+    // the reference opens (truncates) the output file here, coder.h:15-21
+    FILE* f = fopen(c->fname.c_str(), "wb");
+    if (!f) { lic360::set_error("coder: cannot open '%s' for writing", c->fname.c_str()); return LIC360_ERR_CODER; }
+    fclose(f);
+    lic360_coder_start_encoder_mem(c);
+    c->to_file = true;
+    return LIC360_OK;
+}
+
+long lic360_coder_finish_mem(lic360_coder* c) {
+    if (!c->encoding) { lic360::set_error("coder: end_encoder without start_encoder"); return -1; }
+    c->bw.put(1, 1);  // ArithmeticCoder.cpp:152-154
+    c->bw.finish();
+    c->encoding = false;
+    return (long)c->bw.bytes.size();
+}
+
+int lic360_coder_end_encoder(lic360_coder* c) {
+    if (lic360_coder_finish_mem(c) < 0) return LIC360_ERR_CODER;
+    if (c->to_file) {
+        FILE* f = fopen(c->fname.c_str(), "wb");
+        if (!f) { lic360::set_error("coder: cannot open '%s' for writing", c->fname.c_str()); return LIC360_ERR_CODER; }
+        size_t n = fwrite(c->bw.bytes.data(), 1, c->bw.bytes.size(), f);
+        fclose(f);
+        if (n != c->bw.bytes.size()) { lic360::set_error("coder: short write to '%s'", c->fname.c_str()); return LIC360_ERR_CODER; }
+    }
+    return LIC360_OK;
+}
+
+long lic360_coder_get_bytes(lic360_coder* c, uint8_t* out, long cap) {
+    long n = (long)c->bw.bytes.size();
+    if (out && cap > 0) memcpy(out, c->bw.bytes.data(), (size_t)(n < cap ? n : cap));
+    return n;
+}
+
+int lic360_coder_start_decoder_mem(lic360_coder* c, const uint8_t* bytes, long n) {
+    c->input.assign(bytes, bytes + (n > 0 ? n : 0));
+    c->br.reset(c->input.data(), c->input.size());
+    c->low = 0; c->high = kMask;
+    c->code = c->br.get(32);  // ArithmeticCoder.cpp:77-78
+    c->decoding = true; c->encoding = false;
+    return LIC360_OK;
+}
+
+int lic360_coder_start_decoder(lic360_coder* c) {
+    FILE* f = fopen(c->fname.c_str(), "rb");
+    if (!f) { lic360::set_error("coder: cannot open '%s' for reading", c->fname.c_str()); return LIC360_ERR_CODER; }
+    std::vector<uint8_t> buf;
+    uint8_t tmp[65536];
+    size_t n;
+    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    fclose(f);
+    return lic360_coder_start_decoder_mem(c, buf.data(), (long)buf.size());
+}
+
+// coder.cpp:30-47 (mask_host == NULL) and :70-89
+int lic360_coder_encodes(lic360_coder* c, const int32_t* table_host, int ncode, const int32_t* label_host,
+                         const float* mask_host, int num) {
+    if (!c->encoding) { lic360::set_error("coder: encodes without start_encoder"); return LIC360_ERR_CODER; }
+    const size_t stride = (size_t)ncode + 1;
+    for (int i = 0; i < num; i++) {
+        if (mask_host && mask_host[i] < 0.5f) continue;
+        const uint32_t* t = reinterpret_cast<const uint32_t*>(table_host) + i * stride;
+        const uint32_t s = (uint32_t)label_host[i];
+        if (s >= (uint32_t)ncode) { lic360::set_error("coder: symbol %u out of range [0,%d)", s, ncode); return LIC360_ERR_CODER; }
+        int rc = ac_update<false>(c, t[s], t[s + 1], t[ncode]);
+        if (rc) return rc;
+    }
+    return LIC360_OK;
+}
+
+// coder.cpp:49-69 (mask_host == NULL) and :90-114; ArithmeticCoder.cpp:82-116
+int lic360_coder_decodes(lic360_coder* c, const int32_t* table_host, int ncode, const float* mask_host, int num,
+                         float* out_host) {
+    if (!c->decoding) { lic360::set_error("coder: decodes without start_decoder"); return LIC360_ERR_CODER; }
+    const size_t stride = (size_t)ncode + 1;
+    for (int i = 0; i < num; i++) {
+        if (mask_host && mask_host[i] < 0.5f) { out_host[i] = c->fill; continue; }
+        const uint32_t* t = reinterpret_cast<const uint32_t*>(table_host) + i * stride;
+        const uint32_t total = t[ncode];
+        if (total == 0 || total > kMinRange) { lic360::set_error("coder: bad total %u", total); return LIC360_ERR_CODER; }
+        const uint64_t range = c->high - c->low + 1;
+        const uint64_t offset = c->code - c->low;
+        const uint64_t value = ((offset + 1) * total - 1) / range;
+        uint32_t s = 0, e = (uint32_t)ncode;
+        while (e - s > 1) {
+            const uint32_t mid = (s + e) >> 1;
+            if (t[mid] > value) e = mid; else s = mid;
+        }
+        int rc = ac_update<true>(c, t[s], t[s + 1], total);
+        if (rc) return rc;
+        if (c->code < c->low || c->code > c->high) { lic360::set_error("coder: code out of range (corrupt stream or table mismatch)"); return LIC360_ERR_CODER; }
+        out_host[i] = (float)s;
+    }
+    return LIC360_OK;
+}
+
+}  // extern "C"

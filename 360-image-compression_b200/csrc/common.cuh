@@ -1,0 +1,65 @@
+// Shared helpers for the lic360_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/lic360_b200.h"
+
+namespace lic360 {
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids of streaming kernels are sized in multiples of this
+
+void set_error(const char* fmt, ...);
+extern long long g_launches;  // counted by LAUNCH_CHECK
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid for a grid-stride streaming kernel: enough CTAs to cover `work` items with `per_cta` items each,
+// rounded up to a multiple of the SM count and capped at `waves` resident waves.
+inline int stream_grid(size_t work, int per_cta, int ctas_per_sm = 8) {
+    size_t need = (work + per_cta - 1) / per_cta;
+    size_t cap = (size_t)kNumSM * ctas_per_sm;
+    if (need >= cap) return (int)cap;
+    size_t g = ((need + kNumSM - 1) / kNumSM) * kNumSM;
+    if (g == 0) g = kNumSM;
+    return (int)g;
+}
+
+#define LIC360_CHECK_ARG(cond, msg)                        \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            lic360::set_error("%s: %s", __func__, msg);    \
+            return LIC360_ERR_ARG;                         \
+        }                                                  \
+    } while (0)
+
+#define LIC360_CUDA(call)                                                               \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            lic360::set_error("%s: %s -> %s", __func__, #call, cudaGetErrorString(e_)); \
+            return LIC360_ERR_CUDA;                                                     \
+        }                                                                               \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                        \
+    do {                                                                                      \
+        lic360::g_launches++;                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess) {                                                              \
+            lic360::set_error("%s: kernel launch failed -> %s", __func__, cudaGetErrorString(e_)); \
+            return LIC360_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+// wavefront slab of step psum (reference: cconv_dc_cuda.cu:113-117)
+inline void slab_of(const int32_t* plan, int H, int W, int G, int psum, int* start, int* len) {
+    int la = psum >= G ? psum - G + 1 : 0;
+    int lb = psum > H + W - 2 ? H + W - 2 : psum;
+    *start = plan[la];
+    int l = plan[lb + 1] - plan[la];
+    *len = l > 0 ? l : 0;
+}
+
+}  // namespace lic360

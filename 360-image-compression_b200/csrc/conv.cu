@@ -1,0 +1,403 @@
+// Masked 3-D context convolution: encode form (CconvEc, whole frame) and wavefront decode form (CconvDc).
+// Replaces /root/reference/extension/cconv_ec_cuda.cu:54-339 and cconv_dc_cuda.cu:58-398.
+//
+// CANONICAL PER-OUTPUT ARITHMETIC (shared by the EC and DC kernels so that encoder and decoder produce
+// bit-identical fp32 values -- the arithmetic decoder desynchronises otherwise, SURVEY.md s7 hard part 1):
+//
+//   glim(kh,kw) = g_out + 4 - kh - kw                      (mask rule, cconv_ec_cuda.cu:71)
+//   P = 0                                                  "past": input groups g_in <  glim
+//   for j in 0 .. ceil(Cin/16)-1:                          16-channel blocks, ascending
+//       u = 0
+//       for ci in block j (ascending): for kh in 0..4: for kw in 0..4:
+//           if tap inside the image and ci/cin_g < glim:   u = fmaf(x[ci,ph,pw], W[o,ci,kh,kw], u)
+//       P = P + u
+//   Q = 0                                                  "present": g_in == glim (constrain 6 only)
+//   for kh: for kw: if tap inside the image and 0 <= glim < G:
+//       for c in 0..cin_g-1:                               Q = fmaf(x[glim*cin_g+c,ph,pw], W[o,glim*cin_g+c,kh,kw], Q)
+//   out = (P + Q) + bias[o];  PReLU: out > 0 ? out : out*slope[o];  optional residual: out = out + r
+//
+// Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical bits
+// (fmaf(x, 0, u) == u for finite x).  The past/present split keeps the latency-critical same-wavefront terms
+// (<= 25*cin_g MACs) separable from the bulk, which only needs data of earlier steps.
+#include "common.cuh"
+
+namespace lic360 {
+
+constexpr int CB = 16;    // canonical input-channel block
+constexpr int TAPS = 25;  // 5x5
+constexpr int TH = 8, TW = 32, XH = TH + 4, XW = TW + 4;  // EC spatial tile and its halo'd smem tile
+constexpr int EC_CHUNKS = 8;                              // 8 four-channel output chunks (32 channels) per EC block
+constexpr int EC_THREADS = 256;
+constexpr int EC_SMEM_BYTES = (CB * XH * XW + EC_CHUNKS * CB * TAPS * 4) * (int)sizeof(float);
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing: W (nsets,Cout,Cin,5,5) -> Wp [set][chunk][ci][tap][4] (past-masked) and
+//                                           Wq [set][chunk][tap][c][4] (present terms)
+// chunk = g_out * cpg4 + (4-channel chunk inside the group); channels beyond cout_g are zero padding.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wq,
+                                  int nsets, int Cin, int Cout, int G, int constrain) {
+    const int cin_g = Cin / G, cout_g = Cout / G, cpg4 = (cout_g + 3) / 4, nchunk = G * cpg4;
+    const size_t np = (size_t)nsets * nchunk * Cin * TAPS * 4;
+    const size_t nq = (size_t)nsets * nchunk * TAPS * cin_g * 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + nq; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < np) {
+            int q = i % 4;
+            int tap = (i / 4) % TAPS;
+            int ci = (i / (4 * TAPS)) % Cin;
+            int chunk = (i / ((size_t)4 * TAPS * Cin)) % nchunk;
+            int set = i / ((size_t)4 * TAPS * Cin * nchunk);
+            int g_out = chunk / cpg4, oc = (chunk % cpg4) * 4 + q;
+            int glim = g_out + 4 - tap / 5 - tap % 5;
+            float v = 0.f;
+            if (oc < cout_g && ci / cin_g < glim)
+                v = w[(((size_t)set * Cout + g_out * cout_g + oc) * Cin + ci) * TAPS + tap];
+            wp[i] = v;
+        } else {
+            size_t k = i - np;
+            int q = k % 4;
+            int c = (k / 4) % cin_g;
+            int tap = (k / ((size_t)4 * cin_g)) % TAPS;
+            int chunk = (k / ((size_t)4 * cin_g * TAPS)) % nchunk;
+            int set = k / ((size_t)4 * cin_g * TAPS * nchunk);
+            int g_out = chunk / cpg4, oc = (chunk % cpg4) * 4 + q;
+            int glim = g_out + 4 - tap / 5 - tap % 5;
+            float v = 0.f;
+            if (oc < cout_g && constrain == 6 && glim >= 0 && glim < G)
+                v = w[(((size_t)set * Cout + g_out * cout_g + oc) * Cin + glim * cin_g + c) * TAPS + tap];
+            wq[k] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// EC: implicit-GEMM style SIMT kernel. One CTA = 8x32 positions x 32 output channels (8 chunks) of one image.
+// Thread tile = 4 positions (along w) x 2 chunks x 4 channels = 32 accumulators; K loop over 16-channel
+// blocks staged in shared memory (x tile with halo + masked weight tile), 25 taps unrolled.
+// ---------------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const float* x; const float* wp; const float* wq; const float* bias; const float* slope; const float* resid;
+    float* out;
+    int N, Cin, H, W, Cout, G, cin_g, cout_g, cpg4, nchunk, per, has_q;
+};
+
+__global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a) {
+    extern __shared__ float4 smem_f4[];
+    float* xs = reinterpret_cast<float*>(smem_f4);  // [CB][XH][XW]
+    float4* ws4 = smem_f4 + (CB * XH * XW) / 4;     // [EC_CHUNKS][CB][TAPS] float4
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = (tid >> 3) & 7, tz = tid >> 6;
+    const int tiles_w = (a.W + TW - 1) / TW;
+    const int w0 = (blockIdx.x % tiles_w) * TW, h0 = (blockIdx.x / tiles_w) * TH;
+    const int ytile = (int)gridDim.y - 1 - (int)blockIdx.y;  // heaviest (largest g_out) tiles first
+    const int chunk0 = ytile * EC_CHUNKS;
+    const int n = blockIdx.z, set = n / a.per;
+    const int Cin = a.Cin, H = a.H, W = a.W;
+
+    const int last_chunk = min(chunk0 + EC_CHUNKS - 1, a.nchunk - 1);
+    const int lim_tile = min(Cin, (last_chunk / a.cpg4 + 4) * a.cin_g);
+    const int nj = (lim_tile + CB - 1) / CB;
+    const int cA = chunk0 + 2 * tz;
+    const int my_lim = min(Cin, (min(cA + 1, a.nchunk - 1) / a.cpg4 + 4) * a.cin_g);
+
+    float P[2][4][4];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) P[c][p][q] = 0.f;
+
+    const float4* wp4 = reinterpret_cast<const float4*>(a.wp);
+    for (int j = 0; j < nj; j++) {
+        const int cb = min(CB, Cin - j * CB);
+        for (int e = tid; e < cb * XH * XW; e += EC_THREADS) {
+            int ci = e / (XH * XW), r = (e % (XH * XW)) / XW, c = e % XW;
+            int h = h0 + r - 2, w = w0 + c - 2;
+            float v = 0.f;
+            if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(a.x + (((size_t)n * Cin + j * CB + ci) * H + h) * W + w);
+            xs[e] = v;
+        }
+        for (int e = tid; e < EC_CHUNKS * cb * TAPS; e += EC_THREADS) {
+            int ch = e / (cb * TAPS), r = e % (cb * TAPS);
+            int chunk = chunk0 + ch;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chunk < a.nchunk) v = __ldg(wp4 + (((size_t)set * a.nchunk + chunk) * Cin + j * CB) * TAPS + r);
+            ws4[ch * CB * TAPS + r] = v;
+        }
+        __syncthreads();
+        if (j * CB < my_lim) {  // warp-uniform: tz is constant inside a warp
+            float u[2][4][4];
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) u[c][p][q] = 0.f;
+#pragma unroll 1
+            for (int ci = 0; ci < cb; ci++) {
+                const float4* wA = ws4 + ((2 * tz) * CB + ci) * TAPS;
+                const float4* wB = ws4 + ((2 * tz + 1) * CB + ci) * TAPS;
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++) {
+                    const float* xr = xs + (ci * XH + ty + kh) * XW + 4 * tx;
+                    float4 x0 = *reinterpret_cast<const float4*>(xr);
+                    float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+                    float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        float4 a4 = wA[kh * 5 + kw], b4 = wB[kh * 5 + kw];
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            float xx = xv[p + kw];
+                            u[0][p][0] = fmaf(xx, a4.x, u[0][p][0]);
+                            u[0][p][1] = fmaf(xx, a4.y, u[0][p][1]);
+                            u[0][p][2] = fmaf(xx, a4.z, u[0][p][2]);
+                            u[0][p][3] = fmaf(xx, a4.w, u[0][p][3]);
+                            u[1][p][0] = fmaf(xx, b4.x, u[1][p][0]);
+                            u[1][p][1] = fmaf(xx, b4.y, u[1][p][1]);
+                            u[1][p][2] = fmaf(xx, b4.z, u[1][p][2]);
+                            u[1][p][3] = fmaf(xx, b4.w, u[1][p][3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) P[c][p][q] = P[c][p][q] + u[c][p][q];
+        }
+        __syncthreads();
+    }
+
+    // present terms + epilogue
+    const int h = h0 + ty;
+    const float4* wq4 = reinterpret_cast<const float4*>(a.wq);
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+        const int chunk = cA + cc;
+        if (chunk >= a.nchunk || h >= H) continue;
+        const int g_out = chunk / a.cpg4;
+        float Q[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) Q[p][q] = 0.f;
+        if (a.has_q) {
+            for (int kh = 0; kh < 5; kh++) {
+                const int ph = h + kh - 2;
+                if (ph < 0 || ph >= H) continue;
+                for (int kw = 0; kw < 5; kw++) {
+                    const int gq = g_out + 4 - kh - kw;
+                    if (gq < 0 || gq >= a.G) continue;
+                    const float4* wrow = wq4 + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
+                    const float* xrow = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W;
+                    for (int c = 0; c < a.cin_g; c++) {
+                        const float4 w4 = __ldg(wrow + c);
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            const int pw = w0 + 4 * tx + p + kw - 2;
+                            if (pw < 0 || pw >= W) continue;
+                            const float xx = __ldg(xrow + (size_t)c * H * W + pw);
+                            Q[p][0] = fmaf(xx, w4.x, Q[p][0]);
+                            Q[p][1] = fmaf(xx, w4.y, Q[p][1]);
+                            Q[p][2] = fmaf(xx, w4.z, Q[p][2]);
+                            Q[p][3] = fmaf(xx, w4.w, Q[p][3]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int oc = (chunk % a.cpg4) * 4 + q;
+            if (oc >= a.cout_g) continue;
+            const int o = g_out * a.cout_g + oc;
+            const float b = __ldg(a.bias + set * a.Cout + o);
+            const float sl = a.slope ? __ldg(a.slope + set * a.Cout + o) : 0.f;
+            const size_t row = (((size_t)n * a.Cout + o) * H + h) * W;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int w = w0 + 4 * tx + p;
+                if (w >= W) continue;
+                float v = (P[cc][p][q] + Q[p][q]) + b;
+                if (a.slope) v = v > 0.f ? v : v * sl;
+                if (a.resid) v = v + a.resid[row + w];
+                a.out[row + w] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DC: one wavefront step. CTA = 32 slab positions (x) x (nblk past segments + 1 present segment) (y), one
+// 4-channel chunk of each position's output group, one image. Segment partials meet in shared memory and are
+// combined in the canonical order by the y == 0 threads.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, const int32_t* __restrict__ idx, int start,
+                                                      int L, int psum, int nblk) {
+    __shared__ float4 part[32][32];
+    const int tx = threadIdx.x, seg = threadIdx.y;
+    const int l = blockIdx.x * 32 + tx;
+    const int n = blockIdx.z, set = n / a.per;
+    const int Cin = a.Cin, H = a.H, W = a.W, HW = a.H * a.W;
+    const bool valid = l < L;
+    int th = 0, tw = 0;
+    if (valid) { th = __ldg(idx + start + l); tw = __ldg(idx + start + l + HW); }
+    const int tc = psum - th - tw;  // output group of this position in this step
+    const int chunk = tc * a.cpg4 + blockIdx.y;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && tc >= 0 && tc < a.G) {
+        if (seg < nblk) {
+            const int lim = min(Cin, (tc + 4) * a.cin_g);
+            if (seg * CB < lim) {
+                const int cb = min(CB, Cin - seg * CB);
+                const float4* wp4 = reinterpret_cast<const float4*>(a.wp) + (((size_t)set * a.nchunk + chunk) * Cin + seg * CB) * TAPS;
+                const float* xb = a.x + ((size_t)n * Cin + seg * CB) * HW;
+                for (int ci = 0; ci < cb; ci++) {
+                    const int bound = tc + 4 - (seg * CB + ci) / a.cin_g;  // taps with kh+kw < bound are "past"
+                    if (bound <= 0) break;
+#pragma unroll
+                    for (int kh = 0; kh < 5; kh++) {
+                        const int ph = th + kh - 2;
+                        if (ph < 0 || ph >= H) continue;
+#pragma unroll
+                        for (int kw = 0; kw < 5; kw++) {
+                            const int pw = tw + kw - 2;
+                            if (pw < 0 || pw >= W || kh + kw >= bound) continue;
+                            const float xx = xb[(size_t)ci * HW + ph * W + pw];
+                            const float4 w4 = __ldg(wp4 + ci * TAPS + kh * 5 + kw);
+                            u.x = fmaf(xx, w4.x, u.x);
+                            u.y = fmaf(xx, w4.y, u.y);
+                            u.z = fmaf(xx, w4.z, u.z);
+                            u.w = fmaf(xx, w4.w, u.w);
+                        }
+                    }
+                }
+            }
+        } else if (a.has_q) {
+            const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * TAPS * a.cin_g;
+            for (int kh = 0; kh < 5; kh++) {
+                const int ph = th + kh - 2;
+                if (ph < 0 || ph >= H) continue;
+                for (int kw = 0; kw < 5; kw++) {
+                    const int pw = tw + kw - 2;
+                    const int gq = tc + 4 - kh - kw;
+                    if (pw < 0 || pw >= W || gq < 0 || gq >= a.G) continue;
+                    const float* xb = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W + pw;
+                    const float4* wrow = wq4 + (kh * 5 + kw) * a.cin_g;
+                    for (int c = 0; c < a.cin_g; c++) {
+                        const float xx = xb[(size_t)c * HW];
+                        const float4 w4 = __ldg(wrow + c);
+                        u.x = fmaf(xx, w4.x, u.x);
+                        u.y = fmaf(xx, w4.y, u.y);
+                        u.z = fmaf(xx, w4.z, u.z);
+                        u.w = fmaf(xx, w4.w, u.w);
+                    }
+                }
+            }
+        }
+    }
+    part[seg][tx] = u;
+    __syncthreads();
+    if (seg == 0 && valid && tc >= 0 && tc < a.G) {
+        float P[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < nblk; j++) {
+            const float4 v = part[j][tx];
+            P[0] = P[0] + v.x; P[1] = P[1] + v.y; P[2] = P[2] + v.z; P[3] = P[3] + v.w;
+        }
+        const float4 qv = part[nblk][tx];  // zero when !has_q
+        const float Q[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int oc = blockIdx.y * 4 + q;
+            if (oc >= a.cout_g) continue;
+            const int o = tc * a.cout_g + oc;
+            float v = (P[q] + Q[q]) + __ldg(a.bias + set * a.Cout + o);
+            if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
+            const size_t p = (((size_t)n * a.Cout + o) * H + th) * W + tw;
+            if (a.resid) v = v + a.resid[p];
+            a.out[p] = v;
+        }
+    }
+}
+
+static int fill_args(ConvArgs& a, const float* x, const float* wp, const float* wq, const float* bias,
+                     const float* slope, const float* resid, float* out, int N, int Cin, int H, int W, int Cout, int G,
+                     int constrain, int nsets) {
+    if (N <= 0 || Cin <= 0 || Cout <= 0 || G <= 0 || H <= 0 || W <= 0 || nsets <= 0) return 1;
+    if (Cin % G || Cout % G || N % nsets) return 1;
+    if (constrain != 5 && constrain != 6) return 1;
+    a.x = x; a.wp = wp; a.wq = wq; a.bias = bias; a.slope = slope; a.resid = resid; a.out = out;
+    a.N = N; a.Cin = Cin; a.H = H; a.W = W; a.Cout = Cout; a.G = G;
+    a.cin_g = Cin / G; a.cout_g = Cout / G; a.cpg4 = (a.cout_g + 3) / 4; a.nchunk = G * a.cpg4;
+    a.per = N / nsets; a.has_q = constrain == 6;
+    return 0;
+}
+
+}  // namespace lic360
+
+using namespace lic360;
+
+extern "C" size_t lic360_cconv_wp_floats(int nsets, int Cin, int Cout, int G) {
+    int cpg4 = (Cout / G + 3) / 4;
+    return (size_t)nsets * G * cpg4 * Cin * TAPS * 4;
+}
+extern "C" size_t lic360_cconv_wq_floats(int nsets, int Cin, int Cout, int G) {
+    int cpg4 = (Cout / G + 3) / 4;
+    return (size_t)nsets * G * cpg4 * TAPS * (Cin / G) * 4;
+}
+
+extern "C" int lic360_cconv_pack(const float* w_dev, float* wp_dev, float* wq_dev, int nsets, int Cin, int Cout, int G,
+                                 int ksize, int constrain, void* stream) {
+    LIC360_CHECK_ARG(ksize == 5, "only 5x5 context kernels are supported (every reference call site uses 5)");
+    LIC360_CHECK_ARG(constrain == 5 || constrain == 6, "constrain must be 5 (first layer) or 6 (hidden)");
+    LIC360_CHECK_ARG(G > 0 && Cin % G == 0 && Cout % G == 0 && nsets > 0, "channels must be multiples of ngroup");
+    size_t total = lic360_cconv_wp_floats(nsets, Cin, Cout, G) + lic360_cconv_wq_floats(nsets, Cin, Cout, G);
+    cconv_pack_kernel<<<stream_grid(total, 256 * 4), 256, 0, as_stream(stream)>>>(w_dev, wp_dev, wq_dev, nsets, Cin, Cout, G, constrain);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
+
+extern "C" int lic360_cconv_ec_forward(const float* x_dev, const float* wp_dev, const float* wq_dev,
+                                       const float* bias_dev, const float* slope_dev, const float* resid_dev,
+                                       float* out_dev, int N, int Cin, int H, int W, int Cout, int G, int constrain,
+                                       int nsets, void* stream) {
+    ConvArgs a;
+    LIC360_CHECK_ARG(fill_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
+                               constrain, nsets) == 0, "bad shape / constrain");
+    static bool attr_set = false;
+    if (!attr_set) {
+        LIC360_CUDA(cudaFuncSetAttribute(cconv_ec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(((W + TW - 1) / TW) * ((H + TH - 1) / TH), (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, N);
+    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, as_stream(stream)>>>(a);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
+
+extern "C" int lic360_cconv_dc_forward(const float* x_dev, const float* wp_dev, const float* wq_dev,
+                                       const float* bias_dev, const float* slope_dev, const float* resid_dev,
+                                       float* out_dev, int N, int Cin, int H, int W, int Cout, int G, int constrain,
+                                       int nsets, const int32_t* idx_dev, const int32_t* plan_host, int psum,
+                                       void* stream) {
+    ConvArgs a;
+    LIC360_CHECK_ARG(fill_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
+                               constrain, nsets) == 0, "bad shape / constrain");
+    const int nblk = (Cin + CB - 1) / CB;
+    LIC360_CHECK_ARG(nblk + 1 <= 32, "Cin too large for the wavefront kernel (max 496)");
+    const int mod = H + W + G - 2;
+    int start, len;
+    slab_of(plan_host, H, W, G, psum, &start, &len);
+    if (!(psum < mod && len > 0)) return LIC360_OK;  // cconv_dc_cuda.cu:121
+    if (psum == 0)                                   // cconv_dc_cuda.cu:124-126 (stream-ordered here)
+        LIC360_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float) * (size_t)N * Cout * H * W, as_stream(stream)));
+    dim3 grid((len + 31) / 32, a.cpg4, N), block(32, nblk + 1);
+    cconv_dc_kernel<<<grid, block, 0, as_stream(stream)>>>(a, idx_dev, start, len, psum, nblk);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
