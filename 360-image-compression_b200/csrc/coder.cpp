@@ -258,4 +258,28 @@ int lic360_coder_decodes(lic360_coder* c, const int32_t* table_host, int ncode, 
     return LIC360_OK;
 }
 
+// Coder::encode / Coder::decode (main.cpp:134-135, coder.cpp:13-29): one symbol with an explicit total
+int lic360_coder_encode_one(lic360_coder* c, const int32_t* table_host, int ncode, int total, int symbol) {
+    if (!c->encoding) { lic360::set_error("coder: encode without start_encoder"); return LIC360_ERR_CODER; }
+    if (symbol < 0 || symbol >= ncode) { lic360::set_error("coder: symbol %d out of range [0,%d)", symbol, ncode); return LIC360_ERR_CODER; }
+    const uint32_t* t = reinterpret_cast<const uint32_t*>(table_host);
+    return ac_update<false>(c, t[symbol], t[symbol + 1], (uint32_t)total);
+}
+
+int lic360_coder_decode_one(lic360_coder* c, const int32_t* table_host, int ncode, int total, int* symbol) {
+    if (!c->decoding) { lic360::set_error("coder: decode without start_decoder"); return LIC360_ERR_CODER; }
+    const uint32_t* t = reinterpret_cast<const uint32_t*>(table_host);
+    const uint64_t range = c->high - c->low + 1;
+    const uint64_t offset = c->code - c->low;
+    const uint64_t value = ((offset + 1) * (uint32_t)total - 1) / range;
+    uint32_t s = 0, e = (uint32_t)ncode;
+    while (e - s > 1) {
+        const uint32_t mid = (s + e) >> 1;
+        if (t[mid] > value) e = mid; else s = mid;
+    }
+    int rc = ac_update<true>(c, t[s], t[s + 1], (uint32_t)total);
+    *symbol = (int)s;
+    return rc;
+}
+
 }  // extern "C"

@@ -169,6 +169,9 @@ int lic360_coder_encodes(lic360_coder* c, const int32_t* table_host, int ncode, 
                          const float* mask_host /* NULL: encodes, else encodes_mask */, int num);
 int lic360_coder_decodes(lic360_coder* c, const int32_t* table_host, int ncode, const float* mask_host, int num,
                          float* out_host);
+/* Coder.encode / Coder.decode (main.cpp:134-135, coder.cpp:13-29): one symbol, explicit total */
+int lic360_coder_encode_one(lic360_coder* c, const int32_t* table_host, int ncode, int total, int symbol);
+int lic360_coder_decode_one(lic360_coder* c, const int32_t* table_host, int ncode, int total, int* symbol);
 /* in-memory variants used by the fused pipeline and the tests */
 int lic360_coder_start_encoder_mem(lic360_coder* c);
 long lic360_coder_finish_mem(lic360_coder* c);             /* returns byte count */

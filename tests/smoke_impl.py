@@ -1,0 +1,39 @@
+"""__graft_entry__.smoke(): one small invocation of the hot path on cuda:0, checked against the oracle."""
+import os
+import tempfile
+
+import numpy as np
+import torch
+
+
+def run_smoke():
+    import lic360
+    import lic360_codec_ops as ops
+    from oracle import oracle as O
+    from op_cases import BY_NAME
+    from util import rel_err, synthetic_latent, t, n
+
+    dev = "cuda:0"
+    l0 = lic360.launch_count()
+    # 1. one masked context-conv layer: whole-frame (EC) and wavefront (DC) forms against the oracle, EC == DC bitwise
+    ec = BY_NAME["cconv_ec_batch_hidden_g12"].run(lic360, dev)["out"]
+    dc = BY_NAME["cconv_dc_batch_hidden_g12"].run(lic360, dev)["out"]
+    ref = BY_NAME["cconv_ec_batch_hidden_g12"].oracle()["out"]
+    assert rel_err(ec, ref) <= 1e-5, rel_err(ec, ref)
+    assert np.array_equal(ec.view(np.int32), dc.view(np.int32)), "EC != DC"
+    # 2. GMM -> CDF tables
+    c = BY_NAME["gmm_table_full"]
+    got, exp = c.run(lic360, dev)["table"], c.oracle()["table"]
+    assert np.abs(got.astype(np.int64) - exp).max() <= 1 and (np.diff(got, axis=1) > 0).all()
+    # 3. tiny end-to-end code stream: encode -> bitstream -> decode == input
+    q, mask, _ = synthetic_latent(7, H=8, W=16)
+    params = ops.make_entropy_params(48, 4, 3, 3, seed=3, device=dev)
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "code")
+        ops.EntEncoder(lic360, params).encode(t(q, dev), t(mask, dev), fn)
+        rec = n(ops.EntDecoder(lic360, params).decode(t(mask, dev), fn))
+        nbytes = os.path.getsize(fn)
+    assert np.array_equal(rec, q * mask), "round trip failed"
+    torch.cuda.synchronize()
+    print("smoke OK: conv rel err %.2e, EC==DC bitwise, tables within 1 count of the oracle, round trip of %d symbols in %d bytes, %d native launches"
+          % (rel_err(ec, ref), int(mask.sum()), nbytes, lic360.launch_count() - l0))
