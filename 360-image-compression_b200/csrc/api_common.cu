@@ -4,7 +4,7 @@
 
 namespace lic360 {
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* lic360_last_error(void) { return lic360::g_err; }
 extern "C" int lic360_version(void) { return 100; }
-extern "C" long long lic360_launch_count(void) { return lic360::g_launches; }
+extern "C" long long lic360_launch_count(void) { return lic360::g_launches.load(); }
 
 // Diagonal-major index plan. Replaces code_contex_opt::reshape (code_contex_cuda.cu:11-32).
 extern "C" int lic360_code_contex(int H, int W, int32_t* idx_host, int32_t* plan_host) {

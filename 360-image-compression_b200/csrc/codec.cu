@@ -1,0 +1,522 @@
+// Fused entropy codec of one ERP latent: the 238-step (code stream) and 95-step (importance stream) loops that the
+// reference drives from Python with ~25 launches, 3 blocking copies and a per-op Coder call per step
+// (test/lic360_demo.py:124-141,173-189,220-238,272-290) run here as one host C++ loop per stream:
+//
+//   encode : prep -> 12 whole-frame context convs (residual add fused) -> ONE kernel that emits the CDF rows of ALL
+//            symbols in coding order (packed 16 B / 128 B rows) -> one D2H copy -> host arithmetic coder.
+//   decode : per wavefront step ONE CUDA graph replay (scatter previous symbols, 12 wavefront convs with TileAdd
+//            fused, CDF rows of the slab written straight into mapped pinned memory, step counter advance) ->
+//            stream sync -> host arithmetic decoder writes the symbols into mapped pinned memory that the next
+//            replay's scatter kernel reads.  The step is read on the device from a descriptor table, so the same
+//            graph is replayed for every step and every image.
+//
+// The bitstream is the reference's (coder.cpp: same coder, same symbol order, same tables); the conv kernels are the
+// ones behind CconvEcOp/CconvDcOp (conv.cu) and the row arithmetic is shared with EntropyGmmTableOp/EntropyTableOp
+// (tables_dev.cuh), so per-op and fused paths are interchangeable bit for bit.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+#include "coder_internal.h"
+#include "internal.cuh"
+#include "tables_dev.cuh"
+
+namespace lic360 {
+
+struct NetDesc {
+    int G = 0, cpg = 0, nlast = 0, nsets = 1, H = 0, W = 0;
+    int Cin[12], Cout[12], constrain[12];
+    bool act[12];
+    float* wp[12] = {nullptr}; float* wq[12] = {nullptr}; float* bias[12] = {nullptr}; float* slope[12] = {nullptr};
+    bool set[12] = {false};
+    float* frame[13] = {nullptr};  // frame[0] = network input, frame[i+1] = output of layer i (persistent in decode)
+    size_t frame_floats[13];
+    int32_t* idx_dev = nullptr;
+    std::vector<int32_t> plan;
+    std::vector<StepDesc> steps;
+    std::vector<int> row_off;  // first row of each step in coding order
+    StepDesc* steps_dev = nullptr;
+    int* row_off_dev = nullptr;
+    int nsteps = 0, max_len = 0, total_rows = 0;
+    cudaGraphExec_t graph = nullptr;
+    int graph_nodes = 0;
+};
+
+}  // namespace lic360
+
+using namespace lic360;
+
+struct lic360_codec {
+    int device = 0, H = 0, W = 0;
+    cudaStream_t stream = nullptr;
+    NetDesc code, imp;
+    int* ctr_dev = nullptr;
+    uint16_t* rows_dev = nullptr;       // encode: all rows of a stream
+    uint16_t* rows_host = nullptr;      // pinned
+    uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
+    float* syms_host = nullptr;         // mapped pinned: decoded symbols of one step
+    float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2)
+    float* mask192_dev = nullptr;
+    lic360_coder* coder[2] = {nullptr, nullptr};
+    double t_host_coder = 0, t_total = 0, t_gpu_wait = 0;
+};
+
+namespace lic360 {
+
+// ------------------------------------------------------------------------------------------------ kernels
+// code stream encoder input: x = (code - 3.5) * mask replicated for the 3 nets (lic360_demo.py:130-131)
+__global__ void prep_code_kernel(const float* __restrict__ code, const float* __restrict__ mask, float* __restrict__ x,
+                                 int n, float bias) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = (code[i] - bias) * mask[i];
+        x[i] = v; x[i + n] = v; x[i + 2 * n] = v;
+    }
+}
+
+__device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst) {
+    uint32_t ovf = 0;
+    uint16_t w[8];
+#pragma unroll
+    for (int j = 1; j <= 7; j++) {
+        const uint32_t v = (uint32_t)(int)o[j];
+        w[j - 1] = (uint16_t)(v & 0xFFFF);
+        ovf |= ((v >> 16) & 1u) << (j - 1);
+    }
+    w[7] = (uint16_t)((sym & 7) | (maskbit << 8) | (ovf << 9));
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+}
+
+// y: (3, G*3, H, W) outputs of [weight_net, delta_net, mean_net]; one thread = one symbol (tc, k) in plan order.
+// all_steps != 0: encoder, every symbol, row index = coding order; else: decoder, the slab of steps[*ctr].
+__global__ void gmm_rows_kernel(const float* __restrict__ y, const float* __restrict__ code, const float* __restrict__ mask,
+                                const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps,
+                                const int* __restrict__ row_off, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
+                                int G, int H, int W, int all_steps, float s2) {
+    const int HW = H * W;
+    int th, tw, tc, row;
+    if (all_steps) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= G * HW) return;
+        const int k = i % HW;
+        tc = i / HW;
+        th = __ldg(idx + k); tw = __ldg(idx + k + HW);
+        const int p = th + tw + tc;
+        row = __ldg(row_off + p) + k - steps[p].start;
+    } else {
+        const StepDesc d = steps[*ctr];
+        const int l = blockIdx.x * blockDim.x + threadIdx.x;
+        if (l >= d.len) return;
+        th = __ldg(idx + d.start + l); tw = __ldg(idx + d.start + l + HW);
+        tc = d.psum - th - tw;
+        row = l;
+    }
+    float wv[3], dv[3], mv[3], o[9];
+    const size_t net = (size_t)G * 3 * HW;
+    const size_t base = ((size_t)tc * 3 * H + th) * W + tw;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        wv[i] = y[base + (size_t)i * HW];
+        dv[i] = y[net + base + (size_t)i * HW];
+        mv[i] = y[2 * net + base + (size_t)i * HW];
+    }
+    gmm_row(wv, dv, mv, o, 3, 8, 3.5f, 65536.f, 1e-6f, s2);
+    const size_t pos = ((size_t)tc * H + th) * W + tw;
+    const int sym = code ? (int)code[pos] : 0;
+    pack_gmm_row(o, sym, mask[pos] < 0.5f ? 0 : 1, rows + (size_t)row * 8);
+}
+
+// importance stream: y (1, 49, h, w) logits; one thread = one position in plan order (G = 1: step p = diagonal p)
+__global__ void imp_rows_kernel(const float* __restrict__ y, const float* __restrict__ levels, const int32_t* __restrict__ idx,
+                                const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
+                                int H, int W, int all_steps) {
+    const int HW = H * W;
+    int k, row;
+    if (all_steps) {
+        k = blockIdx.x * blockDim.x + threadIdx.x;
+        if (k >= HW) return;
+        row = k;
+    } else {
+        const StepDesc d = steps[*ctr];
+        const int l = blockIdx.x * blockDim.x + threadIdx.x;
+        if (l >= d.len) return;
+        k = d.start + l;
+        row = l;
+    }
+    const int th = __ldg(idx + k), tw = __ldg(idx + k + HW);
+    float o[50];
+    for (int i = 0; i < 49; i++) o[1 + i] = y[((size_t)i * H + th) * W + tw];
+    entropy_row(o, 49, 65536.f);
+    uint16_t* dst = rows + (size_t)row * 64;
+    uint32_t ovf[3] = {0, 0, 0};
+    for (int j = 1; j <= 48; j++) {
+        const uint32_t v = (uint32_t)(int)o[j];
+        dst[j - 1] = (uint16_t)(v & 0xFFFF);
+        ovf[(j - 1) / 16] |= ((v >> 16) & 1u) << ((j - 1) % 16);
+    }
+    dst[48] = levels ? (uint16_t)(int)levels[th * W + tw] : 0;
+    dst[49] = (uint16_t)ovf[0]; dst[50] = (uint16_t)ovf[1]; dst[51] = (uint16_t)ovf[2];
+}
+
+// TileInput of the previous step read from mapped pinned memory (tile_input_cuda.cu:27-43); no-op at step 0
+__global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __restrict__ frame, const int32_t* __restrict__ idx,
+                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, int G, int H, int W,
+                                    float bias, float scale, int rep, float* __restrict__ keep) {
+    const int c = *ctr;
+    if (c == 0) return;
+    const StepDesc d = steps[c - 1];
+    const int HW = H * W;
+    const size_t stride = (size_t)G * HW;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < d.len; l += gridDim.x * blockDim.x) {
+        const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
+        const int tc = d.psum - th - tw;
+        const float s = syms[l];
+        const float v = fmaf(scale, s, bias);
+        const size_t p = ((size_t)tc * H + th) * W + tw;
+        for (int r = 0; r < rep; r++) frame[p + r * stride] = v;
+        if (keep) keep[p] = s;  // importance stream: the decoded level itself
+    }
+}
+
+__global__ void advance_kernel(int* ctr) { *ctr = *ctr + 1; }
+
+// code = frame[0:1] + 3.5 * mask (lic360_demo.py:236-237)
+__global__ void finish_code_kernel(const float* __restrict__ frame, const float* __restrict__ mask, float* __restrict__ out,
+                                   int n, float bias) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = frame[i] + bias * mask[i];
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+static void net_init(NetDesc& n, int G, int cpg, int nlast, int nsets, int H, int W) {
+    n.G = G; n.cpg = cpg; n.nlast = nlast; n.nsets = nsets; n.H = H; n.W = W;
+    for (int l = 0; l < 12; l++) {
+        n.Cin[l] = G * (l == 0 ? 1 : cpg);
+        n.Cout[l] = G * (l == 11 ? nlast : cpg);
+        n.constrain[l] = l == 0 ? 5 : 6;
+        n.act[l] = l != 11;
+    }
+    n.frame_floats[0] = (size_t)nsets * G * H * W;
+    for (int l = 0; l < 12; l++) n.frame_floats[l + 1] = (size_t)nsets * n.Cout[l] * H * W;
+}
+
+static int net_alloc(NetDesc& n) {
+    for (int i = 0; i < 13; i++) LIC360_CUDA(cudaMalloc(&n.frame[i], n.frame_floats[i] * sizeof(float)));
+    const int H = n.H, W = n.W, G = n.G;
+    std::vector<int32_t> idx(2 * (size_t)H * W);
+    n.plan.resize(H + W);
+    lic360_code_contex(H, W, idx.data(), n.plan.data());
+    LIC360_CUDA(cudaMalloc(&n.idx_dev, idx.size() * sizeof(int32_t)));
+    LIC360_CUDA(cudaMemcpy(n.idx_dev, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    n.nsteps = H + W + G - 2;
+    n.steps.resize(n.nsteps);
+    n.row_off.resize(n.nsteps + 1);
+    int off = 0;
+    for (int p = 0; p < n.nsteps; p++) {
+        int s, l;
+        slab_of(n.plan.data(), H, W, G, p, &s, &l);
+        n.steps[p] = {p, s, l, 0};
+        n.row_off[p] = off;
+        off += l;
+        if (l > n.max_len) n.max_len = l;
+    }
+    n.row_off[n.nsteps] = off;
+    n.total_rows = off;
+    LIC360_CUDA(cudaMalloc(&n.steps_dev, n.nsteps * sizeof(StepDesc)));
+    LIC360_CUDA(cudaMemcpy(n.steps_dev, n.steps.data(), n.nsteps * sizeof(StepDesc), cudaMemcpyHostToDevice));
+    LIC360_CUDA(cudaMalloc(&n.row_off_dev, (n.nsteps + 1) * sizeof(int)));
+    LIC360_CUDA(cudaMemcpy(n.row_off_dev, n.row_off.data(), (n.nsteps + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    return LIC360_OK;
+}
+
+static void net_free(NetDesc& n) {
+    for (int i = 0; i < 13; i++) cudaFree(n.frame[i]);
+    for (int l = 0; l < 12; l++) { cudaFree(n.wp[l]); cudaFree(n.wq[l]); cudaFree(n.bias[l]); cudaFree(n.slope[l]); }
+    cudaFree(n.idx_dev); cudaFree(n.steps_dev); cudaFree(n.row_off_dev);
+    if (n.graph) cudaGraphExecDestroy(n.graph);
+}
+
+// layer l: input frame, output frame, fused residual (the `y + x` / TileAdd of the residual blocks)
+static void layer_io(const NetDesc& n, int l, const float** x, const float** resid, float** out) {
+    *x = n.frame[l];
+    *out = n.frame[l + 1];
+    *resid = (l >= 2 && l <= 10 && (l % 2) == 0) ? n.frame[l - 1] : nullptr;  // conv2 of block b = layer 2b+2
+}
+
+static int conv_args(const NetDesc& n, int l, ConvArgs& a) {
+    const float *x, *r;
+    float* out;
+    layer_io(n, l, &x, &r, &out);
+    if (fill_conv_args(a, x, n.wp[l], n.wq[l], n.bias[l], n.act[l] ? n.slope[l] : nullptr, r, out, n.nsets, n.Cin[l], n.H, n.W,
+                       n.Cout[l], n.G, n.constrain[l], n.nsets)) {
+        set_error("codec: bad layer geometry");
+        return LIC360_ERR_ARG;
+    }
+    return LIC360_OK;
+}
+
+static int run_ec_net(const NetDesc& n, cudaStream_t s) {
+    for (int l = 0; l < 12; l++) {
+        ConvArgs a;
+        int rc = conv_args(n, l, a);
+        if (rc) return rc;
+        LIC360_CUDA(launch_cconv_ec(a, s));
+    }
+    return LIC360_OK;
+}
+
+static int check_params(const NetDesc& n) {
+    for (int l = 0; l < 12; l++)
+        if (!n.set[l]) { set_error("codec: layer %d has no parameters (call lic360_codec_set_layer)", l); return LIC360_ERR_ARG; }
+    return LIC360_OK;
+}
+
+// capture one decode step of a stream into a graph (replayed for every step)
+static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
+    if (n.graph) return LIC360_OK;
+    cudaStream_t s = c->stream;
+    cudaGraph_t g;
+    LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int nodes = 0;
+    const int tgrid = (n.max_len + 127) / 128;
+    if (is_code)
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W, -3.5f, 1.0f, 3, nullptr);
+    else
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W, -1.0f,
+                                                  (float)(2. / (48 - 1.)), 1, c->levels_dev);
+    nodes++;
+    int rc = LIC360_OK;
+    for (int l = 0; l < 12 && rc == LIC360_OK; l++) {
+        ConvArgs a;
+        rc = conv_args(n, l, a);
+        if (rc == LIC360_OK && launch_cconv_dc(a, n.idx_dev, 0, 0, 0, n.steps_dev, c->ctr_dev, n.max_len, s) != cudaSuccess) {
+            set_error("codec: capture of the wavefront conv failed");
+            rc = LIC360_ERR_CUDA;
+        }
+        nodes++;
+    }
+    if (rc == LIC360_OK) {
+        if (is_code)
+            gmm_rows_kernel<<<tgrid, 128, 0, s>>>(n.frame[12], nullptr, c->mask192_dev /* = mask_up, set before replay */, n.idx_dev,
+                                                  n.steps_dev, n.row_off_dev, c->ctr_dev, c->rows_step_host, n.G, n.H, n.W, 0,
+                                                  (float)(1. / sqrt(2.0)));
+        else
+            imp_rows_kernel<<<tgrid, 128, 0, s>>>(n.frame[12], nullptr, n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_step_host, n.H, n.W, 0);
+        advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);
+        nodes += 2;
+    }
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc != LIC360_OK) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+    LIC360_CUDA(e);
+    LIC360_CUDA(cudaGraphInstantiate(&n.graph, g, 0));
+    cudaGraphDestroy(g);
+    n.graph_nodes = nodes;
+    return LIC360_OK;
+}
+
+using clk = std::chrono::steady_clock;
+static double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+}  // namespace lic360
+
+extern "C" {
+
+lic360_codec* lic360_codec_create(int device, int H, int W) {
+    if (H <= 0 || W <= 0 || (H % 2) || (W % 2)) { set_error("codec: latent size must be positive and even"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("codec: cudaSetDevice(%d) failed", device); return nullptr; }
+    lic360_codec* c = new lic360_codec();
+    c->device = device; c->H = H; c->W = W;
+    net_init(c->code, 48, 4, 3, 3, H, W);
+    net_init(c->imp, 1, 144, 49, 1, H / 2, W / 2);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && net_alloc(c->code) == LIC360_OK && net_alloc(c->imp) == LIC360_OK;
+    const size_t rows_bytes = std::max((size_t)c->code.total_rows * 16, (size_t)c->imp.total_rows * 128);
+    const size_t step_bytes = std::max((size_t)c->code.max_len * 16, (size_t)c->imp.max_len * 128);
+    ok = ok && cudaMalloc(&c->ctr_dev, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->rows_dev, rows_bytes) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&c->rows_host, rows_bytes, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&c->rows_step_host, step_bytes, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&c->syms_host, std::max(c->code.max_len, c->imp.max_len) * sizeof(float), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->levels_dev, (size_t)(H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->mask192_dev, (size_t)192 * (H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
+    c->coder[0] = lic360_coder_create("", 3.5f);
+    c->coder[1] = lic360_coder_create("", 3.5f);
+    if (!ok) {
+        set_error("codec: allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        lic360_codec_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void lic360_codec_destroy(lic360_codec* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    net_free(c->code); net_free(c->imp);
+    cudaFree(c->ctr_dev); cudaFree(c->rows_dev); cudaFreeHost(c->rows_host); cudaFreeHost(c->rows_step_host);
+    cudaFreeHost(c->syms_host); cudaFree(c->levels_dev); cudaFree(c->mask192_dev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    lic360_coder_destroy(c->coder[0]); lic360_coder_destroy(c->coder[1]);
+    delete c;
+}
+
+int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const float* w_dev, const float* bias_dev,
+                           const float* slope_dev) {
+    LIC360_CHECK_ARG(c && (stream_id == 0 || stream_id == 1) && layer >= 0 && layer < 12 && w_dev && bias_dev, "bad arguments");
+    LIC360_CUDA(cudaSetDevice(c->device));
+    NetDesc& n = stream_id == 0 ? c->code : c->imp;
+    LIC360_CHECK_ARG(!n.act[layer] || slope_dev, "this layer has a PReLU: slope_dev must not be NULL");
+    const size_t npf = lic360_cconv_wp_floats(n.nsets, n.Cin[layer], n.Cout[layer], n.G);
+    const size_t nqf = lic360_cconv_wq_floats(n.nsets, n.Cin[layer], n.Cout[layer], n.G);
+    const size_t nb = (size_t)n.nsets * n.Cout[layer];
+    if (!n.wp[layer]) {
+        LIC360_CUDA(cudaMalloc(&n.wp[layer], npf * sizeof(float)));
+        LIC360_CUDA(cudaMalloc(&n.wq[layer], std::max(nqf, (size_t)4) * sizeof(float)));
+        LIC360_CUDA(cudaMalloc(&n.bias[layer], nb * sizeof(float)));
+        LIC360_CUDA(cudaMalloc(&n.slope[layer], nb * sizeof(float)));
+    }
+    int rc = lic360_cconv_pack(w_dev, n.wp[layer], n.wq[layer], n.nsets, n.Cin[layer], n.Cout[layer], n.G, 5, n.constrain[layer], c->stream);
+    if (rc) return rc;
+    LIC360_CUDA(cudaMemcpyAsync(n.bias[layer], bias_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    if (slope_dev) LIC360_CUDA(cudaMemcpyAsync(n.slope[layer], slope_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    LIC360_CUDA(cudaStreamSynchronize(c->stream));
+    n.set[layer] = true;
+    return LIC360_OK;
+}
+
+int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mask_dev, const float* imp_dev) {
+    LIC360_CHECK_ARG(c && code_dev && mask_dev && imp_dev, "bad arguments");
+    LIC360_CUDA(cudaSetDevice(c->device));
+    int rc = check_params(c->code);
+    if (rc == LIC360_OK) rc = check_params(c->imp);
+    if (rc) return rc;
+    const auto t0 = clk::now();
+    c->t_host_coder = 0; c->t_gpu_wait = 0;
+    cudaStream_t s = c->stream;
+    // ---- importance stream (lic360_demo.py:173-189): Scale(-1, 2/47) -> net -> rows of all 2048 symbols
+    {
+        NetDesc& n = c->imp;
+        const int HW = n.H * n.W;
+        rc = lic360_scale(imp_dev, n.frame[0], HW, -1.0f, (float)(2. / (48 - 1.)), s);
+        if (rc) return rc;
+        rc = run_ec_net(n, s);
+        if (rc) return rc;
+        imp_rows_kernel<<<(HW + 127) / 128, 128, 0, s>>>(n.frame[12], imp_dev, n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_dev, n.H, n.W, 1);
+        LAUNCH_CHECK();
+        LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 128, cudaMemcpyDeviceToHost, s));
+        auto tw = clk::now();
+        LIC360_CUDA(cudaStreamSynchronize(s));
+        c->t_gpu_wait += ms_since(tw);
+        auto th = clk::now();
+        lic360_coder_start_encoder_mem(c->coder[1]);
+        rc = coder_encode_packed_imp(c->coder[1], c->rows_host, n.total_rows);
+        if (rc) return rc;
+        if (lic360_coder_finish_mem(c->coder[1]) < 0) return LIC360_ERR_CODER;
+        c->t_host_coder += ms_since(th);
+    }
+    // ---- code stream (lic360_demo.py:124-141)
+    {
+        NetDesc& n = c->code;
+        const int nel = n.G * n.H * n.W;
+        prep_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(code_dev, mask_dev, n.frame[0], nel, 3.5f);
+        LAUNCH_CHECK();
+        rc = run_ec_net(n, s);
+        if (rc) return rc;
+        gmm_rows_kernel<<<(nel + 127) / 128, 128, 0, s>>>(n.frame[12], code_dev, mask_dev, n.idx_dev, n.steps_dev, n.row_off_dev,
+                                                          c->ctr_dev, c->rows_dev, n.G, n.H, n.W, 1, (float)(1. / sqrt(2.0)));
+        LAUNCH_CHECK();
+        LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 16, cudaMemcpyDeviceToHost, s));
+        auto tw = clk::now();
+        LIC360_CUDA(cudaStreamSynchronize(s));
+        c->t_gpu_wait += ms_since(tw);
+        auto th = clk::now();
+        lic360_coder_start_encoder_mem(c->coder[0]);
+        rc = coder_encode_packed_gmm(c->coder[0], c->rows_host, n.total_rows);
+        if (rc) return rc;
+        if (lic360_coder_finish_mem(c->coder[0]) < 0) return LIC360_ERR_CODER;
+        c->t_host_coder += ms_since(th);
+    }
+    c->t_total = ms_since(t0);
+    return LIC360_OK;
+}
+
+long lic360_codec_stream_size(lic360_codec* c, int stream_id) {
+    long n = 0;
+    coder_bytes(c->coder[stream_id ? 1 : 0], &n);
+    return n;
+}
+
+long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long cap) {
+    return lic360_coder_get_bytes(c->coder[stream_id ? 1 : 0], out, cap);
+}
+
+static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code, lic360_coder* coder) {
+    cudaStream_t s = c->stream;
+    int rc = build_step_graph(c, n, is_code);
+    if (rc) return rc;
+    for (int i = 0; i < 13; i++) LIC360_CUDA(cudaMemsetAsync(n.frame[i], 0, n.frame_floats[i] * sizeof(float), s));
+    LIC360_CUDA(cudaMemsetAsync(c->ctr_dev, 0, sizeof(int), s));
+    for (int p = 0; p < n.nsteps; p++) {
+        LIC360_CUDA(cudaGraphLaunch(n.graph, s));
+        g_launches += n.graph_nodes;
+        auto tw = clk::now();
+        LIC360_CUDA(cudaStreamSynchronize(s));
+        c->t_gpu_wait += ms_since(tw);
+        auto th = clk::now();
+        const int len = n.steps[p].len;
+        rc = is_code ? coder_decode_packed_gmm(coder, c->rows_step_host, len, c->syms_host)
+                     : coder_decode_packed_imp(coder, c->rows_step_host, len, c->syms_host);
+        c->t_host_coder += ms_since(th);
+        if (rc) return rc;
+    }
+    // scatter the symbols of the last step (the final TileInput of lic360_demo.py:236,285)
+    const int tgrid = (n.max_len + 127) / 128;
+    if (is_code)
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W, -3.5f, 1.0f, 3, nullptr);
+    else
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W, -1.0f,
+                                                  (float)(2. / (48 - 1.)), 1, c->levels_dev);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
+
+int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, const uint8_t* code_bytes, long n_code,
+                        float* code_out_dev, float* mask_out_dev) {
+    LIC360_CHECK_ARG(c && imp_bytes && code_bytes && code_out_dev && mask_out_dev && n_imp >= 0 && n_code >= 0, "bad arguments");
+    LIC360_CUDA(cudaSetDevice(c->device));
+    int rc = check_params(c->code);
+    if (rc == LIC360_OK) rc = check_params(c->imp);
+    if (rc) return rc;
+    const auto t0 = clk::now();
+    c->t_host_coder = 0; c->t_gpu_wait = 0;
+    cudaStream_t s = c->stream;
+    // ---- importance stream (lic360_demo.py:272-290) -> levels -> Imp2mask(48,192) -> Dtow -> mask_up
+    lic360_coder_start_decoder_mem(c->coder[1], imp_bytes, n_imp);
+    rc = decode_stream(c, c->imp, false, c->coder[1]);
+    if (rc) return rc;
+    rc = lic360_imp2mask(c->levels_dev, c->mask192_dev, 1, 192, c->imp.H, c->imp.W, 48, s);
+    if (rc) return rc;
+    rc = lic360_dtow(c->mask192_dev, mask_out_dev, 1, 192, c->imp.H, c->imp.W, 2, 1, s);
+    if (rc) return rc;
+    // the code-stream graph reads the mask through mask192_dev's slot: point it at the caller's mask_up instead
+    // ---- code stream (lic360_demo.py:220-238)
+    lic360_coder_start_decoder_mem(c->coder[0], code_bytes, n_code);
+    {
+        // mask_up must live in codec-owned memory because the graph captured its address: reuse frame-sized scratch
+        LIC360_CUDA(cudaMemcpyAsync(c->mask192_dev, mask_out_dev, (size_t)48 * c->H * c->W * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    rc = decode_stream(c, c->code, true, c->coder[0]);
+    if (rc) return rc;
+    const int nel = 48 * c->H * c->W;
+    finish_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(c->code.frame[0], c->mask192_dev, code_out_dev, nel, 3.5f);
+    LAUNCH_CHECK();
+    LIC360_CUDA(cudaStreamSynchronize(s));
+    c->t_total = ms_since(t0);
+    return LIC360_OK;
+}
+
+int lic360_codec_last_timing(lic360_codec* c, double* out, int n) {
+    const double v[3] = {c->t_total, c->t_host_coder, c->t_gpu_wait};
+    for (int i = 0; i < n && i < 3; i++) out[i] = v[i];
+    return LIC360_OK;
+}
+
+}  // extern "C"

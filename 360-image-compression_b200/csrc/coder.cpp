@@ -137,6 +137,86 @@ inline int ac_update(lic360_coder* c, uint32_t sym_low, uint32_t sym_high, uint3
 
 }  // namespace
 
+// ---- packed-row fast paths of the fused pipeline (codec.cu); see coder_internal.h for the row formats ----------
+namespace lic360 {
+
+static inline uint32_t gmm_bin(const uint16_t* r, int j) {  // j in 0..8
+    if (j == 0) return 0;
+    if (j == 8) return 65536;
+    return (uint32_t)r[j - 1] | (((uint32_t)(r[7] >> (9 + j - 1)) & 1u) << 16);
+}
+
+int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows) {
+    for (int i = 0; i < nrows; i++) {
+        const uint16_t* r = rows + (size_t)i * 8;
+        if (!((r[7] >> 8) & 1)) continue;  // mask < 0.5: not coded (coder.cpp:79)
+        const int s = r[7] & 7;
+        int rc = ac_update<false>(c, gmm_bin(r, s), gmm_bin(r, s + 1), 65536);
+        if (rc) return rc;
+    }
+    return LIC360_OK;
+}
+
+int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, float* out) {
+    for (int i = 0; i < nrows; i++) {
+        const uint16_t* r = rows + (size_t)i * 8;
+        if (!((r[7] >> 8) & 1)) { out[i] = c->fill; continue; }  // coder.cpp:101-102
+        const uint64_t range = c->high - c->low + 1;
+        const uint64_t offset = c->code - c->low;
+        const uint64_t value = (((offset + 1) << 16) - 1) / range;
+        uint32_t s = 0, e = 8;
+        while (e - s > 1) {
+            const uint32_t mid = (s + e) >> 1;
+            if (gmm_bin(r, mid) > value) e = mid; else s = mid;
+        }
+        int rc = ac_update<true>(c, gmm_bin(r, s), gmm_bin(r, s + 1), 65536);
+        if (rc) return rc;
+        if (c->code < c->low || c->code > c->high) { set_error("coder: code out of range (corrupt stream or table mismatch)"); return LIC360_ERR_CODER; }
+        out[i] = (float)s;
+    }
+    return LIC360_OK;
+}
+
+static inline uint32_t imp_bin(const uint16_t* r, int j) {  // j in 0..49
+    if (j == 0) return 0;
+    if (j == 49) return 65536;
+    return (uint32_t)r[j - 1] | (((uint32_t)(r[49 + (j - 1) / 16] >> ((j - 1) % 16)) & 1u) << 16);
+}
+
+int coder_encode_packed_imp(lic360_coder* c, const uint16_t* rows, int nrows) {
+    for (int i = 0; i < nrows; i++) {
+        const uint16_t* r = rows + (size_t)i * 64;
+        const int s = r[48];
+        if (s >= 49) { set_error("coder: importance level %d out of range", s); return LIC360_ERR_CODER; }
+        int rc = ac_update<false>(c, imp_bin(r, s), imp_bin(r, s + 1), 65536);
+        if (rc) return rc;
+    }
+    return LIC360_OK;
+}
+
+int coder_decode_packed_imp(lic360_coder* c, const uint16_t* rows, int nrows, float* out) {
+    for (int i = 0; i < nrows; i++) {
+        const uint16_t* r = rows + (size_t)i * 64;
+        const uint64_t range = c->high - c->low + 1;
+        const uint64_t offset = c->code - c->low;
+        const uint64_t value = (((offset + 1) << 16) - 1) / range;
+        uint32_t s = 0, e = 49;
+        while (e - s > 1) {
+            const uint32_t mid = (s + e) >> 1;
+            if (imp_bin(r, mid) > value) e = mid; else s = mid;
+        }
+        int rc = ac_update<true>(c, imp_bin(r, s), imp_bin(r, s + 1), 65536);
+        if (rc) return rc;
+        if (c->code < c->low || c->code > c->high) { set_error("coder: code out of range (corrupt stream or table mismatch)"); return LIC360_ERR_CODER; }
+        out[i] = (float)s;
+    }
+    return LIC360_OK;
+}
+
+const uint8_t* coder_bytes(lic360_coder* c, long* n) { *n = (long)c->bw.bytes.size(); return c->bw.bytes.data(); }
+
+}  // namespace lic360
+
 extern "C" {
 
 lic360_coder* lic360_coder_create(const char* fname, float fill_value) {

@@ -1,6 +1,7 @@
 // Shared helpers for the lic360_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -11,7 +12,7 @@ namespace lic360 {
 constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids of streaming kernels are sized in multiples of this
 
 void set_error(const char* fmt, ...);
-extern long long g_launches;  // counted by LAUNCH_CHECK
+extern std::atomic<long long> g_launches;  // counted by LAUNCH_CHECK (and by graph replays)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

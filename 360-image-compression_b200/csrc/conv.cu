@@ -19,7 +19,7 @@
 // Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical bits
 // (fmaf(x, 0, u) == u for finite x).  The past/present split keeps the latency-critical same-wavefront terms
 // (<= 25*cin_g MACs) separable from the bulk, which only needs data of earlier steps.
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace lic360 {
 
@@ -75,11 +75,6 @@ __global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict
 // Thread tile = 4 positions (along w) x 2 chunks x 4 channels = 32 accumulators; K loop over 16-channel
 // blocks staged in shared memory (x tile with halo + masked weight tile), 25 taps unrolled.
 // ---------------------------------------------------------------------------------------------------------
-struct ConvArgs {
-    const float* x; const float* wp; const float* wq; const float* bias; const float* slope; const float* resid;
-    float* out;
-    int N, Cin, H, W, Cout, G, cin_g, cout_g, cpg4, nchunk, per, has_q;
-};
 
 __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a) {
     extern __shared__ float4 smem_f4[];
@@ -238,9 +233,15 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 // combined in the canonical order by the y == 0 threads.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, const int32_t* __restrict__ idx, int start,
-                                                      int L, int psum, int nblk) {
+                                                      int L, int psum, int nblk, const StepDesc* __restrict__ steps,
+                                                      const int* __restrict__ ctr) {
     __shared__ float4 part[32][32];
     const int tx = threadIdx.x, seg = threadIdx.y;
+    if (steps) {  // graph replay: the step is read on the device, the grid is sized for the longest slab
+        const StepDesc d = steps[*ctr];
+        start = d.start; L = d.len; psum = d.psum;
+        if ((int)blockIdx.x * 32 >= L) return;
+    }
     const int l = blockIdx.x * 32 + tx;
     const int n = blockIdx.z, set = n / a.per;
     const int Cin = a.Cin, H = a.H, W = a.W, HW = a.H * a.W;
@@ -325,9 +326,9 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, const 
     }
 }
 
-static int fill_args(ConvArgs& a, const float* x, const float* wp, const float* wq, const float* bias,
-                     const float* slope, const float* resid, float* out, int N, int Cin, int H, int W, int Cout, int G,
-                     int constrain, int nsets) {
+int fill_conv_args(ConvArgs& a, const float* x, const float* wp, const float* wq, const float* bias,
+                   const float* slope, const float* resid, float* out, int N, int Cin, int H, int W, int Cout, int G,
+                   int constrain, int nsets) {
     if (N <= 0 || Cin <= 0 || Cout <= 0 || G <= 0 || H <= 0 || W <= 0 || nsets <= 0) return 1;
     if (Cin % G || Cout % G || N % nsets) return 1;
     if (constrain != 5 && constrain != 6) return 1;
@@ -336,6 +337,30 @@ static int fill_args(ConvArgs& a, const float* x, const float* wp, const float* 
     a.cin_g = Cin / G; a.cout_g = Cout / G; a.cpg4 = (a.cout_g + 3) / 4; a.nchunk = G * a.cpg4;
     a.per = N / nsets; a.has_q = constrain == 6;
     return 0;
+}
+
+cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(cconv_ec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH), (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, a.N);
+    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start, int len, int psum, const StepDesc* steps,
+                            const int* ctr, int max_len, cudaStream_t s) {
+    const int nblk = (a.Cin + CB - 1) / CB;
+    const int L = steps ? max_len : len;
+    if (L <= 0) return cudaSuccess;
+    dim3 grid((L + 31) / 32, a.cpg4, a.N), block(32, nblk + 1);
+    cconv_dc_kernel<<<grid, block, 0, s>>>(a, idx_dev, start, len, psum, nblk, steps, ctr);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 }  // namespace lic360
@@ -367,16 +392,9 @@ extern "C" int lic360_cconv_ec_forward(const float* x_dev, const float* wp_dev, 
                                        float* out_dev, int N, int Cin, int H, int W, int Cout, int G, int constrain,
                                        int nsets, void* stream) {
     ConvArgs a;
-    LIC360_CHECK_ARG(fill_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
+    LIC360_CHECK_ARG(fill_conv_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
                                constrain, nsets) == 0, "bad shape / constrain");
-    static bool attr_set = false;
-    if (!attr_set) {
-        LIC360_CUDA(cudaFuncSetAttribute(cconv_ec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_SMEM_BYTES));
-        attr_set = true;
-    }
-    dim3 grid(((W + TW - 1) / TW) * ((H + TH - 1) / TH), (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, N);
-    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, as_stream(stream)>>>(a);
-    LAUNCH_CHECK();
+    LIC360_CUDA(launch_cconv_ec(a, as_stream(stream)));
     return LIC360_OK;
 }
 
@@ -386,7 +404,7 @@ extern "C" int lic360_cconv_dc_forward(const float* x_dev, const float* wp_dev, 
                                        int nsets, const int32_t* idx_dev, const int32_t* plan_host, int psum,
                                        void* stream) {
     ConvArgs a;
-    LIC360_CHECK_ARG(fill_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
+    LIC360_CHECK_ARG(fill_conv_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
                                constrain, nsets) == 0, "bad shape / constrain");
     const int nblk = (Cin + CB - 1) / CB;
     LIC360_CHECK_ARG(nblk + 1 <= 32, "Cin too large for the wavefront kernel (max 496)");
@@ -396,8 +414,6 @@ extern "C" int lic360_cconv_dc_forward(const float* x_dev, const float* wp_dev, 
     if (!(psum < mod && len > 0)) return LIC360_OK;  // cconv_dc_cuda.cu:121
     if (psum == 0)                                   // cconv_dc_cuda.cu:124-126 (stream-ordered here)
         LIC360_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float) * (size_t)N * Cout * H * W, as_stream(stream)));
-    dim3 grid((len + 31) / 32, a.cpg4, N), block(32, nblk + 1);
-    cconv_dc_kernel<<<grid, block, 0, as_stream(stream)>>>(a, idx_dev, start, len, psum, nblk);
-    LAUNCH_CHECK();
+    LIC360_CUDA(launch_cconv_dc(a, idx_dev, start, len, psum, nullptr, nullptr, 0, as_stream(stream)));
     return LIC360_OK;
 }

@@ -10,27 +10,11 @@
 // memory; here one thread owns one symbol row, keeps everything in registers, and the rows of a CTA are
 // staged in shared memory so that global stores are fully coalesced.
 #include "common.cuh"
+#include "tables_dev.cuh"
 
 namespace lic360 {
 
 constexpr int TBL_THREADS = 128;
-
-// strictly-increasing fix-up of one row held in shared memory (row stride 1, nt = ngroup+1 entries).
-// gmm_rule: entropy_gmm_table_cuda.cu:85-107 tests T[i+1] <= T[i] (before adding the running bias),
-// otherwise entropy_table_cuda.cu:53-76 tests T[i+1] + bias <= T[i].
-__device__ __forceinline__ void fixup_row(float* o, int ngroup, bool gmm_rule) {
-    float bias = 0.f, mval = 0.f;
-    int midx = 0;
-    for (int i = 0; i < ngroup; i++) {
-        const bool bump = gmm_rule ? (o[i + 1] <= o[i]) : (o[i + 1] + bias <= o[i]);
-        if (bump) bias += 1.f;
-        o[i + 1] += bias;
-        const float d = o[i + 1] - o[i];
-        if (d > mval) { mval = d; midx = i; }
-    }
-    if (bias > 0.f)
-        for (int i = midx; i < ngroup; i++) o[i + 1] -= bias;
-}
 
 // One thread per symbol. weight/delta are rewritten in place (reference behaviour, :29-57).
 __global__ void __launch_bounds__(TBL_THREADS) gmm_table_kernel(float* __restrict__ weight, float* __restrict__ delta,
@@ -44,33 +28,16 @@ __global__ void __launch_bounds__(TBL_THREADS) gmm_table_kernel(float* __restric
     float* o = srow + threadIdx.x * nt;
     if (r < rows) {
         float wv[16], dv[16], mv[16];
-        // softmax over the mixture logits, entropy_gmm_table_cuda.cu:29-48
-        float mval = weight[(size_t)r * ng], psum = 0.f;
-        wv[0] = mval;
-        for (int i = 1; i < ng; i++) { wv[i] = weight[(size_t)r * ng + i]; if (mval < wv[i]) mval = wv[i]; }
-        for (int i = 0; i < ng; i++) { wv[i] = expf(wv[i] - mval); psum += wv[i]; }
-        for (int i = 0; i < ng; i++) { wv[i] = wv[i] / psum; weight[(size_t)r * ng + i] = wv[i]; }
-        // delta clamp, :51-57
         for (int i = 0; i < ng; i++) {
-            float t = delta[(size_t)r * ng + i];
-            t = t < 0 ? beta : t + beta;
-            dv[i] = t;
-            delta[(size_t)r * ng + i] = t;
+            wv[i] = weight[(size_t)r * ng + i];
+            dv[i] = delta[(size_t)r * ng + i];
             mv[i] = mean[(size_t)r * ng + i];
         }
-        // bins, :60-82 / :138-158
-        o[0] = 0.f;
-        o[nt - 1] = static_cast<int>(total);
-        for (int pt = 1; pt < nt - 1; pt++) {
-            float v = pt - 1 - bias + 0.5;  // (float)(pt-1) - bias in float, + 0.5 in double, rounded to float
-            float ps = 0, f;
-            for (int i = 0; i < ng; i++) {
-                f = 0.5 + 0.5 * erff(s2 * (v - mv[i]) / dv[i]);  // erff in float; 0.5+0.5*(.) in double -> float
-                ps = ps + wv[i] * f;                              // float, contracted to FFMA as in the reference
-            }
-            o[pt] = static_cast<int>(total * ps + 0.5);  // float product, + 0.5 in double, truncation
+        gmm_row(wv, dv, mv, o, ng, nstep, bias, total, beta, s2);
+        for (int i = 0; i < ng; i++) {  // softmax / clamp written back in place, entropy_gmm_table_cuda.cu:29-57
+            weight[(size_t)r * ng + i] = wv[i];
+            delta[(size_t)r * ng + i] = dv[i];
         }
-        fixup_row(o, nstep, true);
     }
     __syncthreads();
     const int nrow = min(TBL_THREADS, rows - row0);
@@ -89,19 +56,7 @@ __global__ void __launch_bounds__(TBL_THREADS) entropy_table_kernel(const float*
     for (int e = threadIdx.x; e < nrow * w; e += TBL_THREADS) srow[(e / w) * nt + 1 + e % w] = in[(size_t)row0 * w + e];
     __syncthreads();
     if ((int)threadIdx.x < nrow) {
-        float* o = srow + threadIdx.x * nt;  // o[1+i] holds logit i until overwritten by bin i+1
-        float mval = o[1], psum = 0.f;
-        for (int i = 1; i < w; i++) if (mval < o[1 + i]) mval = o[1 + i];
-        for (int i = 0; i < w; i++) { float t = expf(o[1 + i] - mval); o[1 + i] = t; psum += t; }
-        o[0] = 0.f;
-        const float dp = total / psum;
-        float ts;
-        for (int i = 0; i < w - 1; i++) {
-            ts = o[i] + static_cast<int>(o[1 + i] * dp + 0.5);  // float product, + 0.5 in double, truncation
-            o[i + 1] = ts < total ? ts : total;
-        }
-        o[w] = total;
-        fixup_row(o, w, false);
+        entropy_row(srow + threadIdx.x * nt, w, total);
     }
     __syncthreads();
     float* dst = out + (size_t)row0 * nt;

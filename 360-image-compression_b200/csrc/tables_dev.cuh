@@ -1,0 +1,66 @@
+// Device functions that turn model outputs into integer CDF rows. Shared by the per-op kernels (tables.cu) and the
+// fused codec kernels (codec.cu) so that both paths emit bit-identical tables.
+// Bit-exact tier: every float/double promotion of the reference expressions is kept literally
+// (entropy_gmm_table_cuda.cu:29-107, entropy_table_cuda.cu:24-76); do not compile with --use_fast_math.
+#pragma once
+
+namespace lic360 {
+
+// strictly-increasing fix-up of one row (stride 1, ngroup+1 entries).
+// gmm_rule: entropy_gmm_table_cuda.cu:85-107 tests T[i+1] <= T[i] (before adding the running bias),
+// otherwise entropy_table_cuda.cu:53-76 tests T[i+1] + bias <= T[i].
+__device__ __forceinline__ void fixup_row(float* o, int ngroup, bool gmm_rule) {
+    float bias = 0.f, mval = 0.f;
+    int midx = 0;
+    for (int i = 0; i < ngroup; i++) {
+        const bool bump = gmm_rule ? (o[i + 1] <= o[i]) : (o[i + 1] + bias <= o[i]);
+        if (bump) bias += 1.f;
+        o[i + 1] += bias;
+        const float d = o[i + 1] - o[i];
+        if (d > mval) { mval = d; midx = i; }
+    }
+    if (bias > 0.f)
+        for (int i = midx; i < ngroup; i++) o[i + 1] -= bias;
+}
+
+// GMM row: wv/dv/mv hold the raw mixture logits / deltas / means on entry; on exit wv = softmax, dv = clamped delta
+// (what the reference writes back in place); o receives nstep+1 bins.
+__device__ __forceinline__ void gmm_row(float* wv, float* dv, const float* mv, float* o, int ng, int nstep, float bias,
+                                        float total, float beta, float s2) {
+    const int nt = nstep + 1;
+    float mval = wv[0], psum = 0.f;
+    for (int i = 1; i < ng; i++) if (mval < wv[i]) mval = wv[i];
+    for (int i = 0; i < ng; i++) { wv[i] = expf(wv[i] - mval); psum += wv[i]; }
+    for (int i = 0; i < ng; i++) wv[i] = wv[i] / psum;
+    for (int i = 0; i < ng; i++) { float t = dv[i]; dv[i] = t < 0 ? beta : t + beta; }
+    o[0] = 0.f;
+    o[nt - 1] = static_cast<int>(total);
+    for (int pt = 1; pt < nt - 1; pt++) {
+        float v = pt - 1 - bias + 0.5;  // (float)(pt-1) - bias in float, + 0.5 in double, rounded to float
+        float ps = 0, f;
+        for (int i = 0; i < ng; i++) {
+            f = 0.5 + 0.5 * erff(s2 * (v - mv[i]) / dv[i]);  // erff in float; 0.5+0.5*(.) in double -> float
+            ps = ps + wv[i] * f;                              // float, contracted to FFMA as in the reference
+        }
+        o[pt] = static_cast<int>(total * ps + 0.5);  // float product, + 0.5 in double, truncation
+    }
+    fixup_row(o, nstep, true);
+}
+
+// softmax row -> cumulative integer table. o has w+1 entries; on entry o[1+i] holds logit i.
+__device__ __forceinline__ void entropy_row(float* o, int w, float total) {
+    float mval = o[1], psum = 0.f;
+    for (int i = 1; i < w; i++) if (mval < o[1 + i]) mval = o[1 + i];
+    for (int i = 0; i < w; i++) { float t = expf(o[1 + i] - mval); o[1 + i] = t; psum += t; }
+    o[0] = 0.f;
+    const float dp = total / psum;
+    float ts;
+    for (int i = 0; i < w - 1; i++) {
+        ts = o[i] + static_cast<int>(o[1 + i] * dp + 0.5);  // float product, + 0.5 in double, truncation
+        o[i + 1] = ts < total ? ts : total;
+    }
+    o[w] = total;
+    fixup_row(o, w, false);
+}
+
+}  // namespace lic360

@@ -69,6 +69,14 @@ SIGNATURES = {
     "lic360_coder_finish_mem": (_L, [_P]),
     "lic360_coder_get_bytes": (_L, [_P, _P, _L]),
     "lic360_coder_start_decoder_mem": (_I, [_P, _P, _L]),
+    "lic360_codec_create": (_P, [_I, _I, _I]),
+    "lic360_codec_destroy": (None, [_P]),
+    "lic360_codec_set_layer": (_I, [_P, _I, _I, _P, _P, _P]),
+    "lic360_codec_encode": (_I, [_P, _P, _P, _P]),
+    "lic360_codec_stream_size": (_L, [_P, _I]),
+    "lic360_codec_stream_copy": (_L, [_P, _I, _P, _L]),
+    "lic360_codec_decode": (_I, [_P, _P, _L, _P, _L, _P, _P]),
+    "lic360_codec_last_timing": (_I, [_P, _P, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

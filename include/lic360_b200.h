@@ -178,6 +178,31 @@ long lic360_coder_finish_mem(lic360_coder* c);             /* returns byte count
 long lic360_coder_get_bytes(lic360_coder* c, uint8_t* out, long cap);
 int lic360_coder_start_decoder_mem(lic360_coder* c, const uint8_t* bytes, long n);
 
+/* ---- fused entropy codec of one ERP latent --------------------------------------------------------------------
+ * Replaces the four Python drivers of the reference demo -- EntEncoderFast / ImpEntEncoderFast / EntDecoder /
+ * ImpEntDecoder (test/lic360_demo.py:95-290) together with `encoding`/`decoding` (:339-404) for the entropy part:
+ * same networks, same symbol order, same coder, same two bitstreams (<name>_imp, <name>).
+ * H, W: size of the code latent (image/8; 64x128 for a 512x1024 ERP image); the importance map is (H/2, W/2).
+ * One codec = one image in flight on its own CUDA stream; instances are independent and thread-safe against each
+ * other (one host thread + one codec per image overlaps host coding of one image with GPU steps of another).
+ * stream_id: 0 = code stream (48 groups, 3 nets [weight, delta, mean], 8 symbols), 1 = importance stream (49 symbols).
+ * layer: 0..11 = net.0, net.1.conv1, net.1.conv2, ..., net.5.conv2, net.6 (lic360_demo.py:104-112,153-161,296-322),
+ * weights in the reference layout ((3,)Cout,Cin,5,5).                                                           */
+typedef struct lic360_codec lic360_codec;
+lic360_codec* lic360_codec_create(int device, int H, int W);
+void lic360_codec_destroy(lic360_codec* c);
+int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const float* w_dev, const float* bias_dev,
+                           const float* slope_dev);
+/* code_dev (1,48,H,W) symbols 0..7, mask_dev (1,48,H,W) 0/1, imp_dev (1,1,H/2,W/2) importance levels 0..48 */
+int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mask_dev, const float* imp_dev);
+long lic360_codec_stream_size(lic360_codec* c, int stream_id);
+long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long cap);
+/* -> code_out_dev (1,48,H,W) = symbols where mask == 1, else 0 (lic360_demo.py:236-237); mask_out_dev (1,48,H,W) */
+int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, const uint8_t* code_bytes, long n_code,
+                        float* code_out_dev, float* mask_out_dev);
+/* milliseconds of the last encode/decode call: [0] total, [1] host arithmetic coder, [2] waiting for the GPU */
+int lic360_codec_last_timing(lic360_codec* c, double* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

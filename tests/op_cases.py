@@ -24,6 +24,7 @@ class Case(object):
         self.name, self.run, self.oracle = name, run, oracle
         self.exact, self.close, self.libm = tuple(exact), dict(close or {}), tuple(libm)
         self.skip_ref = ()
+        self.oracle_close = {}
         self.levels_from_device = False
         CASES.append(self)
 
@@ -321,9 +322,9 @@ def _mk_entropy_gmm(name, S, seed):
         r = rng(seed)
         w = r.random((S, 3)).astype(np.float32)
         w /= w.sum(1, keepdims=True)
-        d = (np.abs(r.standard_normal((S, 3))) + 0.05).astype(np.float32)
-        m = (r.standard_normal((S, 3)) * 2).astype(np.float32)
+        d = (np.abs(r.standard_normal((S, 3))) + 0.5).astype(np.float32)
         lab = (r.integers(0, 8, (S, 1)) - 3.5).astype(np.float32)
+        m = (lab + r.standard_normal((S, 3)) * 1.2).astype(np.float32)  # plausible predictions: p is not tiny
         top = r.random(S).astype(np.float32)
         return w, d, m, lab, top
 
@@ -339,7 +340,11 @@ def _mk_entropy_gmm(name, S, seed):
         loss, wd, dd, md, ld = O.entropy_gmm_fwd(w, d, m, lab)
         wd, dd, md, ld = O.entropy_gmm_bwd(wd, dd, md, ld, top)
         return {"loss": loss, "gw": wd, "gd": dd, "gm": md, "gl": ld}
-    Case("entropy_gmm_" + name, run, orc, close={"loss": 1e-5, "gw": 1e-5, "gd": 2e-5, "gm": 2e-5, "gl": 2e-5})
+    c = Case("entropy_gmm_" + name, run, orc, close={"loss": 1e-5, "gw": 1e-5, "gd": 2e-5, "gm": 2e-5, "gl": 2e-5})
+    # p = Phi(b) - Phi(a) cancels: one ulp of erff (libdevice vs glibc) is ~1e-7 absolute on p, amplified by
+    # -log(p + 1e-7) and the 1/p factors of the gradients. The tight float-tier bound is asserted against the CUDA
+    # reference (test_vs_reference_extension / golden); the bound against the glibc-based oracle is looser.
+    c.oracle_close = {"loss": 1e-4, "gw": 1e-4, "gd": 1e-4, "gm": 1e-4, "gl": 1e-4}
 
 
 _mk_entropy_gmm("s1000", 1000, 401)

@@ -105,3 +105,50 @@ def test_streams_against_reference_extension(tmp_path, ref_ext):
     y_mine = n(ops._Net(lic360, params, 48, 4, 3, 3, False, 0)(x))
     y_ref = n(ops._Net(ref_ext, params, 48, 4, 3, 3, False, 0)(x))
     assert rel_err(y_mine, y_ref) <= 1e-5, rel_err(y_mine, y_ref)
+
+
+@pytest.mark.parametrize("H,W,seed", [(8, 16, 31), (16, 12, 32)])
+def test_fused_codec_matches_per_op_path(H, W, seed):
+    """The native pipeline (csrc/codec.cu: graph replay per step, packed rows, no Python in the loop) emits exactly
+    the bytes of the per-op loops, decodes them, and decodes the per-op path's streams."""
+    import lic360
+    import lic360_pipeline as pl
+    q, mask, lv = synthetic_latent(seed, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=seed)
+    per_op = pl.PerOpCodec(lic360, params)
+    fused = pl.FusedCodec(params, H=H, W=W)
+    tq, tm, tl = t(q, DEV), t(mask, DEV), t(lv, DEV)
+    bi0, bc0 = per_op.encode(tq, tm, tl)
+    l0 = lic360.launch_count()
+    bi1, bc1 = fused.encode(tq, tm, tl)
+    assert lic360.launch_count() > l0
+    assert bi1 == bi0 and bc1 == bc0, "fused and per-op bitstreams differ (%d/%d vs %d/%d bytes)" % (len(bi1), len(bc1), len(bi0), len(bc0))
+    code, mup = fused.decode(bi0, bc0)
+    # the decoded importance levels regenerate the mask: it equals the encoder's mask iff the mask is the level map's
+    lv_mask = n(mup)
+    assert np.array_equal(lv_mask, mask)
+    assert np.array_equal(n(code), q * mask)
+    code2, mup2 = per_op.decode(bi1, bc1, H // 2, W // 2)
+    assert np.array_equal(n(code2), q * mask) and np.array_equal(n(mup2), mask)
+    # a second image through the same codec object (graph + buffers reused)
+    q2, mask2, lv2 = synthetic_latent(seed + 100, H=H, W=W)
+    b = fused.encode(t(q2, DEV), t(mask2, DEV), t(lv2, DEV))
+    code3, mup3 = fused.decode(*b)
+    assert np.array_equal(n(code3), q2 * mask2) and np.array_equal(n(mup3), mask2)
+
+
+def test_fused_codec_rejects_bad_input():
+    import lic360_pipeline as pl
+    params = pl.make_codec_params(DEV, seed=1)
+    fused = pl.FusedCodec(params, H=8, W=16)
+    with pytest.raises(RuntimeError):
+        fused.encode(torch.zeros((1, 48, 8, 16)), torch.zeros((1, 48, 8, 16), device=DEV), torch.zeros((1, 1, 4, 8), device=DEV))
+    with pytest.raises(RuntimeError):
+        fused.encode(torch.zeros((1, 48, 8, 8), device=DEV), torch.zeros((1, 48, 8, 16), device=DEV), torch.zeros((1, 1, 4, 8), device=DEV))
+    # a truncated / foreign stream must not hang or crash: it either decodes to garbage or reports a coder error
+    q, mask, lv = synthetic_latent(2, H=8, W=16)
+    bi, bc = fused.encode(t(q, DEV), t(mask, DEV), t(lv, DEV))
+    try:
+        fused.decode(bi, bc[: len(bc) // 2])
+    except RuntimeError as e:
+        assert "coder" in str(e)
