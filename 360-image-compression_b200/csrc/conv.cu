@@ -19,6 +19,7 @@
 // Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical bits
 // (fmaf(x, 0, u) == u for finite x).  The past/present split keeps the latency-critical same-wavefront terms
 // (<= 25*cin_g MACs) separable from the bulk, which only needs data of earlier steps.
+#include <algorithm>
 #include "internal.cuh"
 
 namespace lic360 {
@@ -228,49 +229,69 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// DC: one wavefront step. CTA = 32 slab positions (x) x (nblk past segments + 1 present segment) (y), one
-// 4-channel chunk of each position's output group, one image. Segment partials meet in shared memory and are
-// combined in the canonical order by the y == 0 threads.
+// DC: one wavefront step.  CTA = 32 consecutive positions of ONE anti-diagonal d (so the whole CTA shares the
+// output group tc = psum - d and its weights) x (nblk past segments + 1 present segment) warps, one 4-channel
+// output chunk, one image.  Positions are derived analytically (h = hmin(d) + i, w = d - h), no index plan needed.
+//
+// The 5x5 windows of 32 diagonal neighbours cover a band of 36 rows x 9 columns per input channel
+// (row rr = i + kh, column cc = kh + kw in band coordinates).  Each past-segment warp stages the band of 4 input
+// channels at a time in its private shared-memory slice with row-contiguous (coalesced) global reads, then every
+// lane walks its window from shared memory (stride-9 rows: bank-conflict free) against warp-uniform float4 weight
+// loads.  Segment partials meet in shared memory and are combined in the canonical order by warp 0.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, const int32_t* __restrict__ idx, int start,
-                                                      int L, int psum, int nblk, const StepDesc* __restrict__ steps,
-                                                      const int* __restrict__ ctr) {
-    __shared__ float4 part[32][32];
-    const int tx = threadIdx.x, seg = threadIdx.y;
-    if (steps) {  // graph replay: the step is read on the device, the grid is sized for the longest slab
-        const StepDesc d = steps[*ctr];
-        start = d.start; L = d.len; psum = d.psum;
-        if ((int)blockIdx.x * 32 >= L) return;
-    }
-    const int l = blockIdx.x * 32 + tx;
+constexpr int DC_BAND = 36 * 9;          // cells per channel
+constexpr int DC_STAGE = 4;              // channels staged per round
+constexpr int DC_WARP_FLOATS = DC_STAGE * DC_BAND;
+
+__global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int psum, int nblk, int parts,
+                                                      const StepDesc* __restrict__ steps, const int* __restrict__ ctr) {
+    extern __shared__ float4 dc_smem4[];
+    float4* part = dc_smem4;                                          // [nblk+1][32]
+    float* band_all = reinterpret_cast<float*>(dc_smem4 + (nblk + 1) * 32);  // [nblk][DC_WARP_FLOATS]
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    if (steps) psum = steps[*ctr].psum;  // graph replay: the step is read on the device
+    const int H = a.H, W = a.W, HW = a.H * a.W, Cin = a.Cin;
+    const int la = max(0, psum - a.G + 1), lb = min(psum, H + W - 2);
+    const int d = la + blockIdx.x / parts;
+    if (d > lb) return;
+    const int hmin = max(0, d - W + 1), hmax = min(H - 1, d);
+    const int hbase = hmin + (blockIdx.x % parts) * 32;
+    if (hbase > hmax) return;
+    const int th = hbase + lane, tw = d - th;
+    const bool valid = th <= hmax;
+    const int tc = psum - d;  // output group of this diagonal in this step
     const int n = blockIdx.z, set = n / a.per;
-    const int Cin = a.Cin, H = a.H, W = a.W, HW = a.H * a.W;
-    const bool valid = l < L;
-    int th = 0, tw = 0;
-    if (valid) { th = __ldg(idx + start + l); tw = __ldg(idx + start + l + HW); }
-    const int tc = psum - th - tw;  // output group of this position in this step
     const int chunk = tc * a.cpg4 + blockIdx.y;
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid && tc >= 0 && tc < a.G) {
-        if (seg < nblk) {
-            const int lim = min(Cin, (tc + 4) * a.cin_g);
-            if (seg * CB < lim) {
-                const int cb = min(CB, Cin - seg * CB);
-                const float4* wp4 = reinterpret_cast<const float4*>(a.wp) + (((size_t)set * a.nchunk + chunk) * Cin + seg * CB) * TAPS;
-                const float* xb = a.x + ((size_t)n * Cin + seg * CB) * HW;
-                for (int ci = 0; ci < cb; ci++) {
-                    const int bound = tc + 4 - (seg * CB + ci) / a.cin_g;  // taps with kh+kw < bound are "past"
-                    if (bound <= 0) break;
+    if (seg < nblk) {
+        const int lim = min(Cin, (tc + 4) * a.cin_g);
+        if (seg * CB < lim) {
+            float* band = band_all + seg * DC_WARP_FLOATS;
+            const int cb = min(CB, Cin - seg * CB);
+            const float4* wp4 = reinterpret_cast<const float4*>(a.wp) + (((size_t)set * a.nchunk + chunk) * Cin + seg * CB) * TAPS;
+            const float* xb = a.x + ((size_t)n * Cin + seg * CB) * HW;
+            for (int c0 = 0; c0 < cb; c0 += DC_STAGE) {
+                if (c0 + seg * CB >= lim) break;  // only masked-out channels remain (warp-uniform)
+                const int nc = min(DC_STAGE, cb - c0);
+                __syncwarp();
+                for (int e = lane; e < nc * DC_BAND; e += 32) {
+                    const int ch = e / DC_BAND, r = e % DC_BAND;
+                    const int rr = r / 9, cc = r % 9;
+                    const int row = hbase + rr - 2, col = d - hbase - rr - 2 + cc;
+                    float v = 0.f;
+                    if (row >= 0 && row < H && col >= 0 && col < W) v = xb[(size_t)(c0 + ch) * HW + row * W + col];
+                    band[e] = v;
+                }
+                __syncwarp();
+                for (int ch = 0; ch < nc; ch++) {
+                    const float* bw = band + ch * DC_BAND + lane * 9;
+                    const float4* wrow = wp4 + (c0 + ch) * TAPS;
 #pragma unroll
                     for (int kh = 0; kh < 5; kh++) {
-                        const int ph = th + kh - 2;
-                        if (ph < 0 || ph >= H) continue;
 #pragma unroll
                         for (int kw = 0; kw < 5; kw++) {
-                            const int pw = tw + kw - 2;
-                            if (pw < 0 || pw >= W || kh + kw >= bound) continue;
-                            const float xx = xb[(size_t)ci * HW + ph * W + pw];
-                            const float4 w4 = __ldg(wp4 + ci * TAPS + kh * 5 + kw);
+                            const float xx = bw[kh * 9 + kh + kw];
+                            const float4 w4 = __ldg(wrow + kh * 5 + kw);
                             u.x = fmaf(xx, w4.x, u.x);
                             u.y = fmaf(xx, w4.y, u.y);
                             u.z = fmaf(xx, w4.z, u.z);
@@ -279,38 +300,46 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, const 
                     }
                 }
             }
-        } else if (a.has_q) {
-            const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * TAPS * a.cin_g;
-            for (int kh = 0; kh < 5; kh++) {
-                const int ph = th + kh - 2;
-                if (ph < 0 || ph >= H) continue;
-                for (int kw = 0; kw < 5; kw++) {
-                    const int pw = tw + kw - 2;
-                    const int gq = tc + 4 - kh - kw;
-                    if (pw < 0 || pw >= W || gq < 0 || gq >= a.G) continue;
-                    const float* xb = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W + pw;
-                    const float4* wrow = wq4 + (kh * 5 + kw) * a.cin_g;
-                    for (int c = 0; c < a.cin_g; c++) {
-                        const float xx = xb[(size_t)c * HW];
-                        const float4 w4 = __ldg(wrow + c);
-                        u.x = fmaf(xx, w4.x, u.x);
-                        u.y = fmaf(xx, w4.y, u.y);
-                        u.z = fmaf(xx, w4.z, u.z);
-                        u.w = fmaf(xx, w4.w, u.w);
-                    }
+        }
+    } else if (a.has_q && valid) {
+        const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * TAPS * a.cin_g;
+#pragma unroll 1
+        for (int kh = 0; kh < 5; kh++) {
+            const int ph = th + kh - 2;
+            if (ph < 0 || ph >= H) continue;
+#pragma unroll 1
+            for (int kw = 0; kw < 5; kw++) {
+                const int pw = tw + kw - 2;
+                const int gq = tc + 4 - kh - kw;
+                if (pw < 0 || pw >= W || gq < 0 || gq >= a.G) continue;
+                const float* xq = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W + pw;
+                const float4* wrow = wq4 + (kh * 5 + kw) * a.cin_g;
+                int c = 0;
+                for (; c + 4 <= a.cin_g; c += 4) {  // loads issued together, FMAs in channel order
+                    const float x0 = xq[(size_t)c * HW], x1 = xq[(size_t)(c + 1) * HW], x2 = xq[(size_t)(c + 2) * HW], x3 = xq[(size_t)(c + 3) * HW];
+                    const float4 w0 = __ldg(wrow + c), w1 = __ldg(wrow + c + 1), w2 = __ldg(wrow + c + 2), w3 = __ldg(wrow + c + 3);
+                    u.x = fmaf(x0, w0.x, u.x); u.y = fmaf(x0, w0.y, u.y); u.z = fmaf(x0, w0.z, u.z); u.w = fmaf(x0, w0.w, u.w);
+                    u.x = fmaf(x1, w1.x, u.x); u.y = fmaf(x1, w1.y, u.y); u.z = fmaf(x1, w1.z, u.z); u.w = fmaf(x1, w1.w, u.w);
+                    u.x = fmaf(x2, w2.x, u.x); u.y = fmaf(x2, w2.y, u.y); u.z = fmaf(x2, w2.z, u.z); u.w = fmaf(x2, w2.w, u.w);
+                    u.x = fmaf(x3, w3.x, u.x); u.y = fmaf(x3, w3.y, u.y); u.z = fmaf(x3, w3.z, u.z); u.w = fmaf(x3, w3.w, u.w);
+                }
+                for (; c < a.cin_g; c++) {
+                    const float xx = xq[(size_t)c * HW];
+                    const float4 w4 = __ldg(wrow + c);
+                    u.x = fmaf(xx, w4.x, u.x); u.y = fmaf(xx, w4.y, u.y); u.z = fmaf(xx, w4.z, u.z); u.w = fmaf(xx, w4.w, u.w);
                 }
             }
         }
     }
-    part[seg][tx] = u;
+    part[seg * 32 + lane] = u;
     __syncthreads();
-    if (seg == 0 && valid && tc >= 0 && tc < a.G) {
+    if (seg == 0 && valid) {
         float P[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nblk; j++) {
-            const float4 v = part[j][tx];
+            const float4 v = part[j * 32 + lane];
             P[0] = P[0] + v.x; P[1] = P[1] + v.y; P[2] = P[2] + v.z; P[3] = P[3] + v.w;
         }
-        const float4 qv = part[nblk][tx];  // zero when !has_q
+        const float4 qv = part[nblk * 32 + lane];  // zero when !has_q
         const float Q[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -354,11 +383,20 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
 
 cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start, int len, int psum, const StepDesc* steps,
                             const int* ctr, int max_len, cudaStream_t s) {
+    (void)idx_dev; (void)start; (void)max_len;
     const int nblk = (a.Cin + CB - 1) / CB;
-    const int L = steps ? max_len : len;
-    if (L <= 0) return cudaSuccess;
-    dim3 grid((L + 31) / 32, a.cpg4, a.N), block(32, nblk + 1);
-    cconv_dc_kernel<<<grid, block, 0, s>>>(a, idx_dev, start, len, psum, nblk, steps, ctr);
+    if (!steps && len <= 0) return cudaSuccess;
+    const int parts = (std::min(a.H, a.W) + 31) / 32;          // 32-position chunks per anti-diagonal
+    const int ndiag = std::min(a.G, a.H + a.W - 1);            // a slab holds at most G diagonals
+    const size_t smem = (size_t)(nblk + 1) * 32 * sizeof(float4) + (size_t)nblk * DC_WARP_FLOATS * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(cconv_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    dim3 grid(ndiag * parts, a.cpg4, a.N), block(32, nblk + 1);
+    cconv_dc_kernel<<<grid, block, smem, s>>>(a, psum, nblk, parts, steps, ctr);
     g_launches++;
     return cudaGetLastError();
 }
