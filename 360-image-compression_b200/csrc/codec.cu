@@ -58,7 +58,7 @@ struct lic360_codec {
     float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2)
     float* mask192_dev = nullptr;
     lic360_coder* coder[2] = {nullptr, nullptr};
-    double t_host_coder = 0, t_total = 0, t_gpu_wait = 0;
+    double t_host_coder = 0, t_total = 0, t_gpu_wait = 0, t_imp = 0;
 };
 
 namespace lic360 {
@@ -492,6 +492,7 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     lic360_coder_start_decoder_mem(c->coder[1], imp_bytes, n_imp);
     rc = decode_stream(c, c->imp, false, c->coder[1]);
     if (rc) return rc;
+    c->t_imp = ms_since(t0);
     rc = lic360_imp2mask(c->levels_dev, c->mask192_dev, 1, 192, c->imp.H, c->imp.W, 48, s);
     if (rc) return rc;
     rc = lic360_dtow(c->mask192_dev, mask_out_dev, 1, 192, c->imp.H, c->imp.W, 2, 1, s);
@@ -514,8 +515,8 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
 }
 
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n) {
-    const double v[3] = {c->t_total, c->t_host_coder, c->t_gpu_wait};
-    for (int i = 0; i < n && i < 3; i++) out[i] = v[i];
+    const double v[4] = {c->t_total, c->t_host_coder, c->t_gpu_wait, c->t_imp};
+    for (int i = 0; i < n && i < 4; i++) out[i] = v[i];
     return LIC360_OK;
 }
 

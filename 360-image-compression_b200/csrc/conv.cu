@@ -12,8 +12,12 @@
 //           if tap inside the image and ci/cin_g < glim:   u = fmaf(x[ci,ph,pw], W[o,ci,kh,kw], u)
 //       P = P + u
 //   Q = 0                                                  "present": g_in == glim (constrain 6 only)
-//   for kh: for kw: if tap inside the image and 0 <= glim < G:
-//       for c in 0..cin_g-1:                               Q = fmaf(x[glim*cin_g+c,ph,pw], W[o,glim*cin_g+c,kh,kw], Q)
+//   for jq in 0 .. ceil(cin_g/16)-1:                       16-channel blocks of the group (one block when cin_g <= 16)
+//     q = 0
+//     for c0 in 16*jq, 16*jq+4, ..:                        4-channel chunks of the block
+//       for kh: for kw: if tap inside the image and 0 <= glim < G:
+//         for c in c0 .. min(c0+4, cin_g)-1:               q = fmaf(x[glim*cin_g+c,ph,pw], W[o,glim*cin_g+c,kh,kw], q)
+//     Q = Q + q
 //   out = (P + Q) + bias[o];  PReLU: out > 0 ? out : out*slope[o];  optional residual: out = out + r
 //
 // Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical bits
@@ -183,28 +187,43 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 #pragma unroll
             for (int q = 0; q < 4; q++) Q[p][q] = 0.f;
         if (a.has_q) {
-            for (int kh = 0; kh < 5; kh++) {
-                const int ph = h + kh - 2;
-                if (ph < 0 || ph >= H) continue;
-                for (int kw = 0; kw < 5; kw++) {
-                    const int gq = g_out + 4 - kh - kw;
-                    if (gq < 0 || gq >= a.G) continue;
-                    const float4* wrow = wq4 + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
-                    const float* xrow = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W;
-                    for (int c = 0; c < a.cin_g; c++) {
-                        const float4 w4 = __ldg(wrow + c);
+            for (int jq = 0; jq * CB < a.cin_g; jq++) {
+                float qq[4][4];
 #pragma unroll
-                        for (int p = 0; p < 4; p++) {
-                            const int pw = w0 + 4 * tx + p + kw - 2;
-                            if (pw < 0 || pw >= W) continue;
-                            const float xx = __ldg(xrow + (size_t)c * H * W + pw);
-                            Q[p][0] = fmaf(xx, w4.x, Q[p][0]);
-                            Q[p][1] = fmaf(xx, w4.y, Q[p][1]);
-                            Q[p][2] = fmaf(xx, w4.z, Q[p][2]);
-                            Q[p][3] = fmaf(xx, w4.w, Q[p][3]);
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) qq[p][q] = 0.f;
+                const int cend = min((jq + 1) * CB, a.cin_g);
+                for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+                    const int c1 = min(c0 + 4, cend);
+                    for (int kh = 0; kh < 5; kh++) {
+                        const int ph = h + kh - 2;
+                        if (ph < 0 || ph >= H) continue;
+                        for (int kw = 0; kw < 5; kw++) {
+                            const int gq = g_out + 4 - kh - kw;
+                            if (gq < 0 || gq >= a.G) continue;
+                            const float4* wrow = wq4 + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
+                            const float* xrow = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W;
+                            for (int c = c0; c < c1; c++) {
+                                const float4 w4 = __ldg(wrow + c);
+#pragma unroll
+                                for (int p = 0; p < 4; p++) {
+                                    const int pw = w0 + 4 * tx + p + kw - 2;
+                                    if (pw < 0 || pw >= W) continue;
+                                    const float xx = __ldg(xrow + (size_t)c * H * W + pw);
+                                    qq[p][0] = fmaf(xx, w4.x, qq[p][0]);
+                                    qq[p][1] = fmaf(xx, w4.y, qq[p][1]);
+                                    qq[p][2] = fmaf(xx, w4.z, qq[p][2]);
+                                    qq[p][3] = fmaf(xx, w4.w, qq[p][3]);
+                                }
+                            }
                         }
                     }
                 }
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) Q[p][q] = Q[p][q] + qq[p][q];
             }
         }
 #pragma unroll
@@ -241,13 +260,50 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 // ---------------------------------------------------------------------------------------------------------
 constexpr int DC_BAND = 36 * 9;          // cells per channel
 constexpr int DC_STAGE = 4;              // channels staged per round
-constexpr int DC_WARP_FLOATS = DC_STAGE * DC_BAND;
+constexpr int DC_WARP_FLOATS = DC_STAGE * DC_BAND + DC_STAGE * TAPS * 4;  // band + weights of one stage
 
-__global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int psum, int nblk, int parts,
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0));
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// 100 taps of one stage out of shared memory: x from the band (row stride 9: conflict free), weights broadcast
+// bound0/cin_g: taps with kh + kw >= tc + 4 - group(channel) carry a zero weight and are skipped (warp-uniform)
+__device__ __forceinline__ void dc_stage_fma(const float* band, const float4* wsm, int nc, int lane, int chan0, int cin_g,
+                                             int tc, float4& u) {
+    for (int ch = 0; ch < nc; ch++) {
+        const float* bw = band + ch * DC_BAND + lane * 9;
+        const float4* wrow = wsm + ch * TAPS;
+        const int bound = tc + 4 - (chan0 + ch) / cin_g;
+#pragma unroll
+        for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+            for (int kw = 0; kw < 5; kw++) {
+                if (kh + kw >= bound) continue;
+                const float xx = bw[kh * 9 + kh + kw];
+                const float4 w4 = wrow[kh * 5 + kw];
+                u.x = fmaf(xx, w4.x, u.x);
+                u.y = fmaf(xx, w4.y, u.y);
+                u.z = fmaf(xx, w4.z, u.z);
+                u.w = fmaf(xx, w4.w, u.w);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int psum, int nblk, int nqb, int parts,
                                                       const StepDesc* __restrict__ steps, const int* __restrict__ ctr) {
     extern __shared__ float4 dc_smem4[];
-    float4* part = dc_smem4;                                          // [nblk+1][32]
-    float* band_all = reinterpret_cast<float*>(dc_smem4 + (nblk + 1) * 32);  // [nblk][DC_WARP_FLOATS]
+    const int nseg = nblk + nqb;                                           // past segments then present segments
+    float4* part = dc_smem4;                                               // [nseg][32]
+    int* boff = reinterpret_cast<int*>(dc_smem4 + nseg * 32);              // [DC_BAND] band cell -> row*W+col or -1
+    float* stage_all = reinterpret_cast<float*>(boff + DC_BAND);           // [nseg][DC_WARP_FLOATS]
     const int lane = threadIdx.x, seg = threadIdx.y;
     if (steps) psum = steps[*ctr].psum;  // graph replay: the step is read on the device
     const int H = a.H, W = a.W, HW = a.H * a.W, Cin = a.Cin;
@@ -257,16 +313,25 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
     const int hmin = max(0, d - W + 1), hmax = min(H - 1, d);
     const int hbase = hmin + (blockIdx.x % parts) * 32;
     if (hbase > hmax) return;
+    for (int r = seg * 32 + lane; r < DC_BAND; r += 32 * nseg) {
+        const int rr = r / 9, cc = r % 9;
+        const int row = hbase + rr - 2, col = d - hbase - rr - 2 + cc;
+        boff[r] = (row >= 0 && row < H && col >= 0 && col < W) ? row * W + col : -1;
+    }
+    __syncthreads();
     const int th = hbase + lane, tw = d - th;
     const bool valid = th <= hmax;
     const int tc = psum - d;  // output group of this diagonal in this step
     const int n = blockIdx.z, set = n / a.per;
     const int chunk = tc * a.cpg4 + blockIdx.y;
+    float* band = stage_all + seg * DC_WARP_FLOATS;
+    float4* wsm = reinterpret_cast<float4*>(band + DC_STAGE * DC_BAND);
+    const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
+    const unsigned wsm_s = (unsigned)__cvta_generic_to_shared(wsm);
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
     if (seg < nblk) {
         const int lim = min(Cin, (tc + 4) * a.cin_g);
         if (seg * CB < lim) {
-            float* band = band_all + seg * DC_WARP_FLOATS;
             const int cb = min(CB, Cin - seg * CB);
             const float4* wp4 = reinterpret_cast<const float4*>(a.wp) + (((size_t)set * a.nchunk + chunk) * Cin + seg * CB) * TAPS;
             const float* xb = a.x + ((size_t)n * Cin + seg * CB) * HW;
@@ -274,59 +339,58 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
                 if (c0 + seg * CB >= lim) break;  // only masked-out channels remain (warp-uniform)
                 const int nc = min(DC_STAGE, cb - c0);
                 __syncwarp();
-                for (int e = lane; e < nc * DC_BAND; e += 32) {
-                    const int ch = e / DC_BAND, r = e % DC_BAND;
-                    const int rr = r / 9, cc = r % 9;
-                    const int row = hbase + rr - 2, col = d - hbase - rr - 2 + cc;
-                    float v = 0.f;
-                    if (row >= 0 && row < H && col >= 0 && col < W) v = xb[(size_t)(c0 + ch) * HW + row * W + col];
-                    band[e] = v;
-                }
-                __syncwarp();
                 for (int ch = 0; ch < nc; ch++) {
-                    const float* bw = band + ch * DC_BAND + lane * 9;
-                    const float4* wrow = wp4 + (c0 + ch) * TAPS;
-#pragma unroll
-                    for (int kh = 0; kh < 5; kh++) {
-#pragma unroll
-                        for (int kw = 0; kw < 5; kw++) {
-                            const float xx = bw[kh * 9 + kh + kw];
-                            const float4 w4 = __ldg(wrow + kh * 5 + kw);
-                            u.x = fmaf(xx, w4.x, u.x);
-                            u.y = fmaf(xx, w4.y, u.y);
-                            u.z = fmaf(xx, w4.z, u.z);
-                            u.w = fmaf(xx, w4.w, u.w);
-                        }
+                    const float* xc = xb + (size_t)(c0 + ch) * HW;
+#pragma unroll 4
+                    for (int r = lane; r < DC_BAND; r += 32) {
+                        const int off = boff[r];
+                        cp_async4(band_s + 4u * (ch * DC_BAND + r), off >= 0 ? xc + off : xc, off >= 0);
                     }
                 }
+                for (int e = lane; e < nc * TAPS; e += 32) cp_async16(wsm_s + 16u * e, wp4 + c0 * TAPS + e);
+                cp_async_wait_all();
+                __syncwarp();
+                dc_stage_fma(band, wsm, nc, lane, seg * CB + c0, a.cin_g, tc, u);
             }
         }
-    } else if (a.has_q && valid) {
+    } else if (a.has_q) {
+        // present terms, 16-channel block jq of the group: tap (kh,kw) reads group gq = tc + 4 - (kh+kw) at band column
+        // cc = kh+kw, so the stage holds, for every column cc, the 4-channel chunk [c0, c0+4) of group tc + 4 - cc
+        const int jq = seg - nblk;
+        const int cend = min((jq + 1) * CB, a.cin_g);
         const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * TAPS * a.cin_g;
-#pragma unroll 1
-        for (int kh = 0; kh < 5; kh++) {
-            const int ph = th + kh - 2;
-            if (ph < 0 || ph >= H) continue;
-#pragma unroll 1
-            for (int kw = 0; kw < 5; kw++) {
-                const int pw = tw + kw - 2;
-                const int gq = tc + 4 - kh - kw;
-                if (pw < 0 || pw >= W || gq < 0 || gq >= a.G) continue;
-                const float* xq = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W + pw;
-                const float4* wrow = wq4 + (kh * 5 + kw) * a.cin_g;
-                int c = 0;
-                for (; c + 4 <= a.cin_g; c += 4) {  // loads issued together, FMAs in channel order
-                    const float x0 = xq[(size_t)c * HW], x1 = xq[(size_t)(c + 1) * HW], x2 = xq[(size_t)(c + 2) * HW], x3 = xq[(size_t)(c + 3) * HW];
-                    const float4 w0 = __ldg(wrow + c), w1 = __ldg(wrow + c + 1), w2 = __ldg(wrow + c + 2), w3 = __ldg(wrow + c + 3);
-                    u.x = fmaf(x0, w0.x, u.x); u.y = fmaf(x0, w0.y, u.y); u.z = fmaf(x0, w0.z, u.z); u.w = fmaf(x0, w0.w, u.w);
-                    u.x = fmaf(x1, w1.x, u.x); u.y = fmaf(x1, w1.y, u.y); u.z = fmaf(x1, w1.z, u.z); u.w = fmaf(x1, w1.w, u.w);
-                    u.x = fmaf(x2, w2.x, u.x); u.y = fmaf(x2, w2.y, u.y); u.z = fmaf(x2, w2.z, u.z); u.w = fmaf(x2, w2.w, u.w);
-                    u.x = fmaf(x3, w3.x, u.x); u.y = fmaf(x3, w3.y, u.y); u.z = fmaf(x3, w3.z, u.z); u.w = fmaf(x3, w3.w, u.w);
+        const float* xn = a.x + (size_t)n * Cin * HW;
+        for (int c0 = jq * CB; c0 < cend; c0 += DC_STAGE) {
+            const int nc = min(DC_STAGE, cend - c0);
+            __syncwarp();
+            for (int ch = 0; ch < nc; ch++) {
+#pragma unroll 4
+                for (int r = lane; r < DC_BAND; r += 32) {
+                    const int off = boff[r];
+                    const int gq = tc + 4 - r % 9;
+                    const bool ok = off >= 0 && gq >= 0 && gq < a.G;
+                    cp_async4(band_s + 4u * (ch * DC_BAND + r), ok ? xn + (size_t)(gq * a.cin_g + c0 + ch) * HW + off : xn, ok);
                 }
-                for (; c < a.cin_g; c++) {
-                    const float xx = xq[(size_t)c * HW];
-                    const float4 w4 = __ldg(wrow + c);
-                    u.x = fmaf(xx, w4.x, u.x); u.y = fmaf(xx, w4.y, u.y); u.z = fmaf(xx, w4.z, u.z); u.w = fmaf(xx, w4.w, u.w);
+            }
+            // weights of this chunk: wq layout [tap][cin_g] float4 -> stage layout [ch][tap]
+            for (int e = lane; e < nc * TAPS; e += 32) cp_async16(wsm_s + 16u * e, wq4 + (e % TAPS) * a.cin_g + c0 + e / TAPS);
+            cp_async_wait_all();
+            __syncwarp();
+            // canonical order inside the chunk is (kh, kw, c): channel innermost
+#pragma unroll
+            for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+                for (int kw = 0; kw < 5; kw++) {
+                    const int gq = tc + 4 - kh - kw;
+                    if (gq < 0 || gq >= a.G) continue;  // warp-uniform
+                    for (int ch = 0; ch < nc; ch++) {
+                        const float xx = band[ch * DC_BAND + (lane + kh) * 9 + kh + kw];
+                        const float4 w4 = wsm[ch * TAPS + kh * 5 + kw];
+                        u.x = fmaf(xx, w4.x, u.x);
+                        u.y = fmaf(xx, w4.y, u.y);
+                        u.z = fmaf(xx, w4.z, u.z);
+                        u.w = fmaf(xx, w4.w, u.w);
+                    }
                 }
             }
         }
@@ -339,8 +403,11 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
             const float4 v = part[j * 32 + lane];
             P[0] = P[0] + v.x; P[1] = P[1] + v.y; P[2] = P[2] + v.z; P[3] = P[3] + v.w;
         }
-        const float4 qv = part[nblk * 32 + lane];  // zero when !has_q
-        const float Q[4] = {qv.x, qv.y, qv.z, qv.w};
+        float Q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = nblk; j < nseg; j++) {  // zero partials when !has_q
+            const float4 v = part[j * 32 + lane];
+            Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int oc = blockIdx.y * 4 + q;
@@ -388,15 +455,18 @@ cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start
     if (!steps && len <= 0) return cudaSuccess;
     const int parts = (std::min(a.H, a.W) + 31) / 32;          // 32-position chunks per anti-diagonal
     const int ndiag = std::min(a.G, a.H + a.W - 1);            // a slab holds at most G diagonals
-    const size_t smem = (size_t)(nblk + 1) * 32 * sizeof(float4) + (size_t)nblk * DC_WARP_FLOATS * sizeof(float);
+    const int nqb = a.has_q ? (a.cin_g + CB - 1) / CB : 1;
+    const int nseg = nblk + nqb;
+    if (nseg > 32) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)nseg * 32 * sizeof(float4) + DC_BAND * sizeof(int) + (size_t)nseg * DC_WARP_FLOATS * sizeof(float);
     static size_t attr_smem = 0;
     if (smem > 48 * 1024 && smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(cconv_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
-    dim3 grid(ndiag * parts, a.cpg4, a.N), block(32, nblk + 1);
-    cconv_dc_kernel<<<grid, block, smem, s>>>(a, psum, nblk, parts, steps, ctr);
+    dim3 grid(ndiag * parts, a.cpg4, a.N), block(32, nseg);
+    cconv_dc_kernel<<<grid, block, smem, s>>>(a, psum, nblk, nqb, parts, steps, ctr);
     g_launches++;
     return cudaGetLastError();
 }
@@ -445,7 +515,7 @@ extern "C" int lic360_cconv_dc_forward(const float* x_dev, const float* wp_dev, 
     LIC360_CHECK_ARG(fill_conv_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
                                constrain, nsets) == 0, "bad shape / constrain");
     const int nblk = (Cin + CB - 1) / CB;
-    LIC360_CHECK_ARG(nblk + 1 <= 32, "Cin too large for the wavefront kernel (max 496)");
+    LIC360_CHECK_ARG(nblk + (Cin / G + CB - 1) / CB <= 32, "Cin too large for the wavefront kernel");
     const int mod = H + W + G - 2;
     int start, len;
     slab_of(plan_host, H, W, G, psum, &start, &len);

@@ -81,7 +81,7 @@ class FusedCodec(object):
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
+        if h and LIB is not None:
             LIB.lic360_codec_destroy(h)
             self._h = None
 
@@ -115,6 +115,6 @@ class FusedCodec(object):
         return code, mask
 
     def last_timing(self):
-        out = (ctypes.c_double * 3)()
-        LIB.lic360_codec_last_timing(self._h, out, 3)
-        return {'total_ms': out[0], 'host_coder_ms': out[1], 'gpu_wait_ms': out[2]}
+        out = (ctypes.c_double * 4)()
+        LIB.lic360_codec_last_timing(self._h, out, 4)
+        return {'total_ms': out[0], 'host_coder_ms': out[1], 'gpu_wait_ms': out[2], 'imp_stream_ms': out[3]}
