@@ -58,7 +58,8 @@ struct lic360_codec {
     float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2)
     float* mask192_dev = nullptr;
     lic360_coder* coder[2] = {nullptr, nullptr};
-    double t_host_coder = 0, t_total = 0, t_gpu_wait = 0, t_imp = 0;
+    double t_host_coder = 0, t_total = 0, t_gpu_wait = 0, t_imp = 0, t_gpu_steps = 0, t_gpu_steps_imp = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace lic360 {
@@ -327,6 +328,7 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
     net_init(c->code, 48, 4, 3, 3, H, W);
     net_init(c->imp, 1, 144, 49, 1, H / 2, W / 2);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
     ok = ok && net_alloc(c->code) == LIC360_OK && net_alloc(c->imp) == LIC360_OK;
     const size_t rows_bytes = std::max((size_t)c->code.total_rows * 16, (size_t)c->imp.total_rows * 128);
     const size_t step_bytes = std::max((size_t)c->code.max_len * 16, (size_t)c->imp.max_len * 128);
@@ -353,6 +355,8 @@ void lic360_codec_destroy(lic360_codec* c) {
     net_free(c->code); net_free(c->imp);
     cudaFree(c->ctr_dev); cudaFree(c->rows_dev); cudaFreeHost(c->rows_host); cudaFreeHost(c->rows_step_host);
     cudaFreeHost(c->syms_host); cudaFree(c->levels_dev); cudaFree(c->mask192_dev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
     lic360_coder_destroy(c->coder[0]); lic360_coder_destroy(c->coder[1]);
     delete c;
@@ -455,11 +459,17 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code, lic360_coder
     for (int i = 0; i < 13; i++) LIC360_CUDA(cudaMemsetAsync(n.frame[i], 0, n.frame_floats[i] * sizeof(float), s));
     LIC360_CUDA(cudaMemsetAsync(c->ctr_dev, 0, sizeof(int), s));
     for (int p = 0; p < n.nsteps; p++) {
+        LIC360_CUDA(cudaEventRecord(c->ev0, s));
         LIC360_CUDA(cudaGraphLaunch(n.graph, s));
+        LIC360_CUDA(cudaEventRecord(c->ev1, s));
         g_launches += n.graph_nodes;
         auto tw = clk::now();
         LIC360_CUDA(cudaStreamSynchronize(s));
         c->t_gpu_wait += ms_since(tw);
+        float ems = 0.f;
+        cudaEventElapsedTime(&ems, c->ev0, c->ev1);  // device time of this step's graph replay, on the codec stream
+        c->t_gpu_steps += ems;
+        if (!is_code) c->t_gpu_steps_imp += ems;
         auto th = clk::now();
         const int len = n.steps[p].len;
         rc = is_code ? coder_decode_packed_gmm(coder, c->rows_step_host, len, c->syms_host)
@@ -486,7 +496,7 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     if (rc == LIC360_OK) rc = check_params(c->imp);
     if (rc) return rc;
     const auto t0 = clk::now();
-    c->t_host_coder = 0; c->t_gpu_wait = 0;
+    c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0;
     cudaStream_t s = c->stream;
     // ---- importance stream (lic360_demo.py:272-290) -> levels -> Imp2mask(48,192) -> Dtow -> mask_up
     lic360_coder_start_decoder_mem(c->coder[1], imp_bytes, n_imp);
@@ -515,8 +525,8 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
 }
 
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n) {
-    const double v[4] = {c->t_total, c->t_host_coder, c->t_gpu_wait, c->t_imp};
-    for (int i = 0; i < n && i < 4; i++) out[i] = v[i];
+    const double v[6] = {c->t_total, c->t_host_coder, c->t_gpu_wait, c->t_imp, c->t_gpu_steps, c->t_gpu_steps_imp};
+    for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
     return LIC360_OK;
 }
 

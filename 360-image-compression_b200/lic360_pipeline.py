@@ -115,6 +115,7 @@ class FusedCodec(object):
         return code, mask
 
     def last_timing(self):
-        out = (ctypes.c_double * 4)()
-        LIB.lic360_codec_last_timing(self._h, out, 4)
-        return {'total_ms': out[0], 'host_coder_ms': out[1], 'gpu_wait_ms': out[2], 'imp_stream_ms': out[3]}
+        out = (ctypes.c_double * 6)()
+        LIB.lic360_codec_last_timing(self._h, out, 6)
+        return {'total_ms': out[0], 'host_coder_ms': out[1], 'gpu_wait_ms': out[2], 'imp_stream_ms': out[3],
+                'gpu_steps_ms': out[4], 'imp_gpu_steps_ms': out[5]}

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- ERP Mpx/s, entropy encode+decode of the LIC360 context-model path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A step = one pass of the hot path over one synthetic 512x1024 ERP image per GPU (BASELINE.json configs[1], batch 1):
+importance stream + code stream ENCODE to the two bitstreams, then DECODE back to the latent, through the fused native
+codec (360-image-compression_b200/csrc/codec.cu).  Every rank codes its own image (independent bitstreams, no
+collective on the codec path), so scaling is weak: value = N * 0.524288 Mpx * K / max-over-ranks time.
+
+`value`  : inputs resident in HBM, outputs left in HBM.
+`e2e`    : the same call with the latent in pinned HOST memory: H2D of (code, mask, importance levels) and D2H of the
+           decoded (code, mask) inside the timed region.
+`roofline`: dominant kernel = the wavefront context conv (cconv_dc_kernel, 12 launches per decode step).
+`cpu_baseline` / `--impl reference`: the CPU rendition (oracle/: OpenMP restatement of the conv/table ops + the
+           reference's own host arithmetic coder when oracle/_ref is built) on a bounded sample, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "360-image-compression_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "_ref")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+MPX = 512 * 1024 / 1e6
+H, W, G = 64, 128, 48  # code latent of a 512x1024 image
+
+
+def synthetic_latent(seed, h=H, w=W):
+    from util import synthetic_latent as mk
+    return mk(seed, H=h, W=w)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic work
+def dc_algorithmic_bytes():
+    """Algorithmic bytes of one wavefront-conv launch, averaged over the 12 layers x 238 steps of one code-stream
+    decode: non-zero weights of the output groups present in the slab (read once), the inputs that carry
+    a non-zero weight for at least one slab output (read once), the slab outputs (written once); fp32, 3 nets."""
+    import numpy as np
+    npos = np.zeros(H + W - 1, np.int64)
+    for d in range(H + W - 1):
+        npos[d] = min(d, H - 1) - max(0, d - W + 1) + 1
+    layers = [(1, 4, 5)] + [(4, 4, 6)] * 10 + [(4, 3, 6)]
+    total, launches = 0, 0
+    for cin, cout, con in layers:
+        # non-zero weights per output group g: taps (kh,kw) x allowed input groups
+        nnz_g = np.zeros(G, np.int64)
+        for g in range(G):
+            for s in range(9):  # s = kh + kw, number of taps with that sum
+                ntap = min(s, 8 - s) + 1
+                allowed = g + 4 - s + (1 if con == 6 else 0)
+                nnz_g[g] += ntap * max(0, min(G, allowed)) * cin * cout
+        for psum in range(H + W + G - 2):
+            la, lb = max(0, psum - G + 1), min(psum, H + W - 2)
+            groups = [psum - d for d in range(la, lb + 1)]
+            wbytes = 4 * 3 * sum(int(nnz_g[g]) for g in groups)
+            obytes = 4 * 3 * cout * int(npos[la:lb + 1].sum())
+            ibytes = 0
+            for e in range(max(0, la - 4), min(H + W - 2, lb + 4) + 1):
+                ng = psum - e + (1 if con == 6 else 0)
+                ibytes += 4 * 3 * cin * int(npos[e]) * max(0, min(G, ng))
+            total += wbytes + obytes + ibytes
+            launches += 1
+    return total / launches, launches
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(steps, warmup, sample_hw=(16, 32)):
+    """CPU rendition on a bounded sample: one (8*h)x(8*w)-pixel ERP image worth of latent, all host threads."""
+    import numpy as np
+    import torch
+    from oracle import cpu_codec
+    import lic360_codec_ops as ops
+    h, w = sample_hw
+    q, mask, lv = synthetic_latent(2024, h, w)
+    params = {'code': ops.make_entropy_params(48, 4, 3, 3, 2024, 'cpu'), 'imp': ops.make_entropy_params(1, 144, 49, None, 2025, 'cpu')}
+    codec = cpu_codec.CpuCodec(cpu_codec.params_to_numpy(params))
+    px = (8 * h) * (8 * w) / 1e6
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        bi, bc = codec.encode(q, mask, lv)
+        code, m = codec.decode(bi, bc, h // 2, w // 2)
+        times.append(time.time() - t0)
+        assert np.array_equal(code, q * mask) and np.array_equal(m, mask)
+    t = sum(times[warmup:]) / max(1, steps)
+    from oracle import oracle as O
+    return {"value": px / t, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%dx%d-pixel ERP latent (1,48,%d,%d)+(1,1,%d,%d), encode+decode, OpenMP oracle conv/tables + %s host coder, %.1f s/step"
+                      % (8 * h, 8 * w, h, w, h // 2, w // 2, "reference" if O.have_ref_coder() else "restated", t)}, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-ext", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        # reference arm: the CPU implementation of the path on the host cores; rank 0 alone runs it
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, t = cpu_arm(steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": cb["value"], "unit": "Mpx/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: 512x1024 ERP entropy encode+decode, batch 1 -- bounded CPU sample: " + cb["sample"]},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import lic360
+    import lic360_pipeline as pl
+
+    q, mask, lv = synthetic_latent(2024 + rank)
+    params = pl.make_codec_params(dev, seed=2024)
+    codec = pl.FusedCodec(params, H=H, W=W, gid=local_rank)
+    host = [torch.from_numpy(a).pin_memory() for a in (q, mask, lv)]
+    tq, tm, tl = [h.to(dev) for h in host]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, e2e):
+        nbytes, timing = None, {"enc": [], "dec": []}
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between iterations
+            if e2e:
+                a, b, c = [h.to(dev, non_blocking=True) for h in host]
+            else:
+                a, b, c = tq, tm, tl
+            bi, bc = codec.encode(a, b, c)
+            timing["enc"].append(codec.last_timing())
+            code, mup = codec.decode(bi, bc)
+            timing["dec"].append(codec.last_timing())
+            if e2e:
+                code_h, mask_h = code.cpu(), mup.cpu()
+            nbytes = (len(bi), len(bc))
+        return nbytes, timing, (code, mup)
+
+    def timed(steps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lic360.launch_count()
+        e0.record()
+        nbytes, timing, outs = run(steps, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), nbytes, timing, outs, lic360.launch_count() - l0
+
+    run(warmup, False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, nbytes, timing, outs, launches = timed(args.steps, False)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    ok = bool(torch.equal(outs[0], tq * tm)) and bool(torch.equal(outs[1], tm))
+    run(1, True)
+    ms_e2e, _, _, _, _ = timed(args.steps, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * MPX * args.steps / (ms / 1e3)
+    e2e_value = world * MPX * args.steps / (ms_e2e / 1e3)
+    mean = lambda k, xs: sum(x[k] for x in xs) / len(xs)
+    # ---- roofline of the dominant kernel
+    alg_bytes, n_dc_code = dc_algorithmic_bytes()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "dc_kernel_summary.json")))
+    except Exception:
+        pass
+    gpu_steps_ms = mean("gpu_steps_ms", timing["dec"])
+    code_share = 1.0 - mean("imp_gpu_steps_ms", timing["dec"]) / max(gpu_steps_ms, 1e-9)
+    dc_share = prof.get("dc_share_of_step", 0.95)
+    dc_launch_us = gpu_steps_ms * code_share * dc_share / n_dc_code * 1e3
+    achieved = alg_bytes / (dc_launch_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "cconv_dc_kernel (wavefront context conv, code stream)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_us": dc_launch_us, "launches_per_decode": n_dc_code,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "note": "launch time = CUDA-event time of the decode graph replays on the codec stream x kernel share from profiles/ (see DESIGN.md s5)"}
+    line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: 512x1024 ERP entropy encode+decode (importance + code stream), batch 1 per GPU, model-idx-3 shape, seeded random-init weights",
+                       "latent": [1, 48, H, W], "images_per_gpu_per_step": 1, "l2": "256 MB buffer written between iterations (L2 flush)",
+                       "parallelism": "image-sharded, no collective"},
+            "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
+                    "d2h_bytes_per_step": int(2 * tq.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "breakdown_ms": {"encode": mean("total_ms", timing["enc"]), "encode_host_coder": mean("host_coder_ms", timing["enc"]),
+                             "decode": mean("total_ms", timing["dec"]), "decode_host_coder": mean("host_coder_ms", timing["dec"]),
+                             "decode_importance_stream": mean("imp_stream_ms", timing["dec"]), "decode_gpu_graph_replays": gpu_steps_ms},
+            "bitstream": {"imp_bytes": nbytes[0], "code_bytes": nbytes[1], "bpp": (nbytes[0] + nbytes[1]) * 8 / (512 * 1024), "round_trip_exact": ok}}
+    if sampler:
+        line["clocks"] = sampler.summary()
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"], _ = cpu_arm(1, 0)
+        except Exception as e:  # the CPU arm is a reported baseline; never let it take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+    if world == 1 and not args.no_ref_ext:
+        # reported baseline A: the unmodified reference CUDA extension rebuilt for sm_100, same loops
+        try:
+            import lic360_ref
+            ref = pl.PerOpCodec(lic360_ref, params, gid=local_rank)
+            ref.encode(tq, tm, tl)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            rbi, rbc = ref.encode(tq, tm, tl)
+            rc, rm = ref.decode(rbi, rbc, H // 2, W // 2)
+            torch.cuda.synchronize()
+            t1 = time.time()
+            line["reference_cuda_ext"] = {"value": MPX / (t1 - t0), "unit": "Mpx/s", "ms_per_step": (t1 - t0) * 1e3, "imp_bytes": len(rbi), "code_bytes": len(rbc),
+                                          "identical_bytes_to_b200": (rbi, rbc) == tuple(codec.encode(tq, tm, tl)), "round_trip_exact": bool(torch.equal(rc, tq * tm)),
+                                          "note": "oracle/_ref/lic360_ref*.so driven by the per-op loops of lic360_demo.py; reported, not the target"}
+        except Exception as e:
+            line["reference_cuda_ext"] = {"unavailable": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

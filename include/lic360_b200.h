@@ -201,7 +201,7 @@ long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long
 int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, const uint8_t* code_bytes, long n_code,
                         float* code_out_dev, float* mask_out_dev);
 /* milliseconds of the last encode/decode call: [0] total, [1] host arithmetic coder, [2] waiting for the GPU,
- * [3] importance stream part of a decode */
+ * [3] importance stream part of a decode, [4] CUDA-event time of all decode graph replays, [5] of the importance stream ones */
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n);
 
 #ifdef __cplusplus
