@@ -4,11 +4,14 @@
 //
 //   encode : prep -> 12 whole-frame context convs (residual add fused) -> ONE kernel that emits the CDF rows of ALL
 //            symbols in coding order (packed 16 B / 128 B rows) -> one D2H copy -> host arithmetic coder.
-//   decode : per wavefront step ONE CUDA graph replay (scatter previous symbols, 12 wavefront convs with TileAdd
-//            fused, CDF rows of the slab written straight into mapped pinned memory, step counter advance) ->
-//            stream sync -> host arithmetic decoder writes the symbols into mapped pinned memory that the next
-//            replay's scatter kernel reads.  The step is read on the device from a descriptor table, so the same
-//            graph is replayed for every step and every image.
+//   decode : per wavefront step ONE CUDA graph replay with two branches (wavefront.cu):
+//              critical branch : scatter previous symbols -> previous-wavefront terms of all 12 layers (one launch) ->
+//                                12-layer chain of same-wavefront terms (one cluster launch per step, TileAdd fused) ->
+//                                CDF rows of the slab written straight into mapped pinned memory + completion flag
+//              side branch     : old terms of ALL 12 layers of the NEXT step (one TMA-fed launch)
+//            The host spins on the flag (no stream sync: the side branch may still be running), runs the arithmetic
+//            decoder and writes the symbols into mapped pinned memory that the next replay's scatter kernel reads.
+//            The step is read on the device from a counter, so the same graph is replayed for every step and image.
 //
 // The bitstream is the reference's (coder.cpp: same coder, same symbol order, same tables); the conv kernels are the
 // ones behind CconvEcOp/CconvDcOp (conv.cu) and the row arithmetic is shared with EntropyGmmTableOp/EntropyTableOp
@@ -20,6 +23,7 @@
 #include "coder_internal.h"
 #include "internal.cuh"
 #include "tables_dev.cuh"
+#include "wavefront.cuh"
 
 namespace lic360 {
 
@@ -40,6 +44,8 @@ struct NetDesc {
     int nsteps = 0, max_len = 0, total_rows = 0;
     cudaGraphExec_t graph = nullptr;
     int graph_nodes = 0;
+    WfEngine wf;       // decoder form of the network (wavefront.cu)
+    double t_kernel[5] = {0, 0, 0, 0, 0};  // profile mode: ms in old / prev / chain / scatter+rows kernels, steps
 };
 
 }  // namespace lic360
@@ -48,7 +54,11 @@ using namespace lic360;
 
 struct lic360_codec {
     int device = 0, H = 0, W = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof[6] = {nullptr};
+    int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
+    int* done_dev = nullptr;            // CTA counter of the rows kernel
+    int mode = 0;                       // 0: pipelined graph replay, 1: serialized launches with per-kernel event timing
     NetDesc code, imp;
     int* ctr_dev = nullptr;
     uint16_t* rows_dev = nullptr;       // encode: all rows of a stream
@@ -158,32 +168,106 @@ __global__ void imp_rows_kernel(const float* __restrict__ y, const float* __rest
     dst[49] = (uint16_t)ovf[0]; dst[50] = (uint16_t)ovf[1]; dst[51] = (uint16_t)ovf[2];
 }
 
-// TileInput of the previous step read from mapped pinned memory (tile_input_cuda.cu:27-43); no-op at step 0
-__global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __restrict__ frame, const int32_t* __restrict__ idx,
-                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, int G, int H, int W,
-                                    float bias, float scale, int rep, float* __restrict__ keep) {
+// TileInput of the previous step read from mapped pinned memory (tile_input_cuda.cu:27-43) into both layouts of the
+// engine's input frame, replicated for the nsets nets; no-op at step 0
+__global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __restrict__ fp0, float* __restrict__ fc0,
+                                    const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps, const int* __restrict__ ctr,
+                                    int G, int H, int W, int D, int HS, int Dp, int Hp, float bias, float scale, int rep,
+                                    float* __restrict__ keep) {
     const int c = *ctr;
     if (c == 0) return;
     const StepDesc d = steps[c - 1];
     const int HW = H * W;
-    const size_t stride = (size_t)G * HW;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < d.len; l += gridDim.x * blockDim.x) {
         const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
         const int tc = d.psum - th - tw;
         const float s = syms[l];
         const float v = fmaf(scale, s, bias);
-        const size_t p = ((size_t)tc * H + th) * W + tw;
-        for (int r = 0; r < rep; r++) frame[p + r * stride] = v;
-        if (keep) keep[p] = s;  // importance stream: the decoded level itself
+        for (int r = 0; r < rep; r++) {
+            fp0[wf_fp_index(D, HS, G, r, tc, th + tw, th)] = v;
+            fc0[wf_fc_index(Dp, Hp, G, r, th + tw, th) + tc] = v;
+        }
+        if (keep) keep[th * W + tw] = s;  // importance stream: the decoded level itself
     }
 }
 
 __global__ void advance_kernel(int* ctr) { *ctr = *ctr + 1; }
 
-// code = frame[0:1] + 3.5 * mask (lic360_demo.py:236-237)
-__global__ void finish_code_kernel(const float* __restrict__ frame, const float* __restrict__ mask, float* __restrict__ out,
-                                   int n, float bias) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = frame[i] + bias * mask[i];
+// code = frame[0:1] + 3.5 * mask (lic360_demo.py:236-237), gathered from the channel-last engine frame
+__global__ void finish_code_kernel(const float* __restrict__ fc0, const float* __restrict__ mask, float* __restrict__ out,
+                                   int G, int H, int W, int Dp, int Hp, float bias) {
+    const int n = G * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int w = i % W, h = (i / W) % H, g = i / (W * H);
+        out[i] = fc0[wf_fc_index(Dp, Hp, G, 0, h + w, h) + g] + bias * mask[i];
+    }
+}
+
+// all rows of a step are in mapped pinned memory: the last CTA raises the host flag
+__device__ __forceinline__ void rows_done(int* done, volatile int* flag, int step) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            *flag = step + 1;
+        }
+    }
+}
+
+// decoder: CDF rows of the slab of step *ctr from the engine's last frame (channel-last, 3 nets x G*3 channels)
+__global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __restrict__ mask, const int32_t* __restrict__ idx,
+                                   const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
+                                   int G, int H, int W, int Dp, int Hp, float s2, int* done, int* flag) {
+    const int step = *ctr;
+    const StepDesc d = steps[step];
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < d.len) {
+        const int HW = H * W;
+        const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
+        const int tc = d.psum - th - tw;
+        const int C = G * 3;
+        float wv[3], dv[3], mv[3], o[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            wv[i] = y[wf_fc_index(Dp, Hp, C, 0, th + tw, th) + tc * 3 + i];
+            dv[i] = y[wf_fc_index(Dp, Hp, C, 1, th + tw, th) + tc * 3 + i];
+            mv[i] = y[wf_fc_index(Dp, Hp, C, 2, th + tw, th) + tc * 3 + i];
+        }
+        gmm_row(wv, dv, mv, o, 3, 8, 3.5f, 65536.f, 1e-6f, s2);
+        const size_t pos = ((size_t)tc * H + th) * W + tw;
+        pack_gmm_row(o, 0, mask[pos] < 0.5f ? 0 : 1, rows + (size_t)l * 8);
+    }
+    rows_done(done, flag, step);
+}
+
+__device__ __forceinline__ void pack_imp_row(const float* o, int sym, uint16_t* dst) {
+    uint32_t ovf[3] = {0, 0, 0};
+    for (int j = 1; j <= 48; j++) {
+        const uint32_t v = (uint32_t)(int)o[j];
+        dst[j - 1] = (uint16_t)(v & 0xFFFF);
+        ovf[(j - 1) / 16] |= ((v >> 16) & 1u) << ((j - 1) % 16);
+    }
+    dst[48] = (uint16_t)sym;
+    dst[49] = (uint16_t)ovf[0]; dst[50] = (uint16_t)ovf[1]; dst[51] = (uint16_t)ovf[2];
+}
+
+__global__ void imp_rows_wf_kernel(const float* __restrict__ y, const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps,
+                                   const int* __restrict__ ctr, uint16_t* __restrict__ rows, int H, int W, int Dp, int Hp, int* done,
+                                   int* flag) {
+    const int step = *ctr;
+    const StepDesc d = steps[step];
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < d.len) {
+        const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + H * W);
+        float o[50];
+        const float* yp = y + wf_fc_index(Dp, Hp, 49, 0, th + tw, th);
+        for (int i = 0; i < 49; i++) o[1 + i] = yp[i];
+        entropy_row(o, 49, 65536.f);
+        pack_imp_row(o, 0, rows + (size_t)l * 64);
+    }
+    rows_done(done, flag, step);
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers
@@ -270,46 +354,80 @@ static int check_params(const NetDesc& n) {
     return LIC360_OK;
 }
 
+// the kernels of one decode step, in stream order on `s` (critical branch); the old terms of the NEXT step go to `side`
+// when it is a different stream (graph capture: a parallel branch) -- they only read wavefronts <= p-1, complete once
+// the scatter of step p-1's symbols has run.
+// ev != nullptr: profile mode, events bracket the kernel classes (everything on `s`).
+#define WF_DEBUG_SYNC(what)                                                                               \
+    do {                                                                                                \
+        if (dbg) {                                                                                      \
+            cudaError_t e_ = cudaStreamSynchronize(s);                                                  \
+            if (e_ != cudaSuccess) { set_error("codec: %s failed -> %s", what, cudaGetErrorString(e_)); return LIC360_ERR_CUDA; } \
+        }                                                                                               \
+    } while (0)
+
+static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s, cudaStream_t side, cudaEvent_t* ev) {
+    const WfNetDev& w = n.wf.dev;
+    static const bool dbg_env = getenv("LIC360_DEBUG_SYNC") != nullptr;
+    const bool dbg = dbg_env && ev != nullptr;  // only in the serialized mode
+    const int tgrid = (n.max_len + 127) / 128;
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[0], s));
+    if (is_code)
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
+    else
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
+    LAUNCH_CHECK();
+    if (side != s) {
+        // fork AFTER the scatter: the old terms of step p+1 read the symbols of wavefront p-1 that it just wrote
+        LIC360_CUDA(cudaEventRecord(c->ev_fork, s));
+        LIC360_CUDA(cudaStreamWaitEvent(side, c->ev_fork, 0));
+        LIC360_CUDA(wf_launch_old(n.wf, 1, side));
+        LIC360_CUDA(cudaEventRecord(c->ev_join, side));
+    }
+    WF_DEBUG_SYNC("scatter kernel");
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
+    LIC360_CUDA(wf_launch_prev(n.wf, s));
+    WF_DEBUG_SYNC("previous-wavefront kernel");
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[2], s));
+    LIC360_CUDA(wf_launch_chain(n.wf, s));
+    WF_DEBUG_SYNC("chain kernel");
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
+    if (is_code)
+        gmm_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], c->mask192_dev /* = mask_up, set before the first step */, n.idx_dev,
+                                                 n.steps_dev, c->ctr_dev, c->rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
+                                                 (float)(1. / sqrt(2.0)), c->done_dev, c->flag_host);
+    else
+        imp_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_step_host, n.H, n.W, w.Dp, w.Hp,
+                                                 c->done_dev, c->flag_host);
+    LAUNCH_CHECK();
+    WF_DEBUG_SYNC("rows kernel");
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
+    if (side != s) LIC360_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    else LIC360_CUDA(wf_launch_old(n.wf, 1, s));
+    WF_DEBUG_SYNC("old-term kernel");
+    if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
+    advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
+
 // capture one decode step of a stream into a graph (replayed for every step)
 static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
     if (n.graph) return LIC360_OK;
     cudaStream_t s = c->stream;
     cudaGraph_t g;
+    const long long l0 = g_launches;
     LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int nodes = 0;
-    const int tgrid = (n.max_len + 127) / 128;
-    if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W, -3.5f, 1.0f, 3, nullptr);
-    else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W, -1.0f,
-                                                  (float)(2. / (48 - 1.)), 1, c->levels_dev);
-    nodes++;
-    int rc = LIC360_OK;
-    for (int l = 0; l < 12 && rc == LIC360_OK; l++) {
-        ConvArgs a;
-        rc = conv_args(n, l, a);
-        if (rc == LIC360_OK && launch_cconv_dc(a, n.idx_dev, 0, 0, 0, n.steps_dev, c->ctr_dev, n.max_len, s) != cudaSuccess) {
-            set_error("codec: capture of the wavefront conv failed");
-            rc = LIC360_ERR_CUDA;
-        }
-        nodes++;
-    }
-    if (rc == LIC360_OK) {
-        if (is_code)
-            gmm_rows_kernel<<<tgrid, 128, 0, s>>>(n.frame[12], nullptr, c->mask192_dev /* = mask_up, set before replay */, n.idx_dev,
-                                                  n.steps_dev, n.row_off_dev, c->ctr_dev, c->rows_step_host, n.G, n.H, n.W, 0,
-                                                  (float)(1. / sqrt(2.0)));
-        else
-            imp_rows_kernel<<<tgrid, 128, 0, s>>>(n.frame[12], nullptr, n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_step_host, n.H, n.W, 0);
-        advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);
-        nodes += 2;
-    }
+    const int rc = launch_step(c, n, is_code, s, c->side, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &g);
+    n.graph_nodes = (int)(g_launches - l0);
+    g_launches = l0;  // captured, not launched: replays are counted in decode_stream
     if (rc != LIC360_OK) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
     LIC360_CUDA(e);
     LIC360_CUDA(cudaGraphInstantiate(&n.graph, g, 0));
     cudaGraphDestroy(g);
-    n.graph_nodes = nodes;
     return LIC360_OK;
 }
 
@@ -327,12 +445,24 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
     c->device = device; c->H = H; c->W = W;
     net_init(c->code, 48, 4, 3, 3, H, W);
     net_init(c->imp, 1, 144, 49, 1, H / 2, W / 2);
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // the critical branch of a decode step runs at the highest priority, the next step's old terms at the lowest
+    bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 6; i++) ok = ok && cudaEventCreate(&c->ev_prof[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->ctr_dev, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->done_dev, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&c->flag_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
     ok = ok && net_alloc(c->code) == LIC360_OK && net_alloc(c->imp) == LIC360_OK;
+    ok = ok && wf_init(c->code.wf, 48, 4, 3, 3, H, W, c->code.idx_dev, c->code.steps_dev, c->ctr_dev, c->code.nsteps, c->code.max_len) == LIC360_OK;
+    ok = ok && wf_init(c->imp.wf, 1, 144, 49, 1, H / 2, W / 2, c->imp.idx_dev, c->imp.steps_dev, c->ctr_dev, c->imp.nsteps, c->imp.max_len) == LIC360_OK;
+    const bool wf_ok = ok;
     const size_t rows_bytes = std::max((size_t)c->code.total_rows * 16, (size_t)c->imp.total_rows * 128);
     const size_t step_bytes = std::max((size_t)c->code.max_len * 16, (size_t)c->imp.max_len * 128);
-    ok = ok && cudaMalloc(&c->ctr_dev, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->rows_dev, rows_bytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(&c->rows_host, rows_bytes, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&c->rows_step_host, step_bytes, cudaHostAllocMapped) == cudaSuccess;
@@ -342,7 +472,7 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
     c->coder[0] = lic360_coder_create("", 3.5f);
     c->coder[1] = lic360_coder_create("", 3.5f);
     if (!ok) {
-        set_error("codec: allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        if (wf_ok) set_error("codec: allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));  // else: wf_init's message
         lic360_codec_destroy(c);
         return nullptr;
     }
@@ -353,6 +483,12 @@ void lic360_codec_destroy(lic360_codec* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     net_free(c->code); net_free(c->imp);
+    wf_free(c->code.wf); wf_free(c->imp.wf);
+    cudaFree(c->done_dev); cudaFreeHost(c->flag_host);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 6; i++) if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
+    if (c->side) cudaStreamDestroy(c->side);
     cudaFree(c->ctr_dev); cudaFree(c->rows_dev); cudaFreeHost(c->rows_host); cudaFreeHost(c->rows_step_host);
     cudaFreeHost(c->syms_host); cudaFree(c->levels_dev); cudaFree(c->mask192_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -382,6 +518,8 @@ int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const floa
     LIC360_CUDA(cudaMemcpyAsync(n.bias[layer], bias_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     if (slope_dev) LIC360_CUDA(cudaMemcpyAsync(n.slope[layer], slope_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     LIC360_CUDA(cudaStreamSynchronize(c->stream));
+    wf_set_layer(n.wf, layer, n.wp[layer], n.wq[layer], n.bias[layer], n.act[layer] ? n.slope[layer] : nullptr);
+    if (n.graph) { cudaGraphExecDestroy(n.graph); n.graph = nullptr; }  // the graph holds the kernel parameters by value
     n.set[layer] = true;
     return LIC360_OK;
 }
@@ -452,24 +590,55 @@ long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long
     return lic360_coder_get_bytes(c->coder[stream_id ? 1 : 0], out, cap);
 }
 
+// wait for the rows of step p without synchronising the stream (the side branch of the graph may still be running)
+static int wait_rows(lic360_codec* c, int p) {
+    volatile int* f = c->flag_host;
+    const auto t0 = clk::now();
+    for (unsigned spins = 1; *f != p + 1; spins++) {
+        if ((spins & 0x3FFF) == 0) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*f == p + 1) break;
+                set_error("codec: step %d finished without producing its rows", p);
+                return LIC360_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) { set_error("codec: step %d failed -> %s", p, cudaGetErrorString(e)); return LIC360_ERR_CUDA; }
+            if (ms_since(t0) > 20000.) { set_error("codec: step %d timed out", p); return LIC360_ERR_CUDA; }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return LIC360_OK;
+}
+
 static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code, lic360_coder* coder) {
     cudaStream_t s = c->stream;
-    int rc = build_step_graph(c, n, is_code);
+    int rc = c->mode == 0 ? build_step_graph(c, n, is_code) : LIC360_OK;
     if (rc) return rc;
-    for (int i = 0; i < 13; i++) LIC360_CUDA(cudaMemsetAsync(n.frame[i], 0, n.frame_floats[i] * sizeof(float), s));
+    *c->flag_host = 0;
+    LIC360_CUDA(wf_clear(n.wf, s));
     LIC360_CUDA(cudaMemsetAsync(c->ctr_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(c->done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(wf_launch_old(n.wf, 0, s));  // old terms of step 0 (all zero, but it keeps the schedule uniform)
+    if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
     for (int p = 0; p < n.nsteps; p++) {
-        LIC360_CUDA(cudaEventRecord(c->ev0, s));
-        LIC360_CUDA(cudaGraphLaunch(n.graph, s));
-        LIC360_CUDA(cudaEventRecord(c->ev1, s));
-        g_launches += n.graph_nodes;
         auto tw = clk::now();
-        LIC360_CUDA(cudaStreamSynchronize(s));
+        if (c->mode == 0) {
+            LIC360_CUDA(cudaGraphLaunch(n.graph, s));
+            g_launches += n.graph_nodes;
+            rc = wait_rows(c, p);
+            if (rc) return rc;
+        } else {
+            rc = launch_step(c, n, is_code, s, s, c->ev_prof);
+            if (rc) return rc;
+            LIC360_CUDA(cudaStreamSynchronize(s));
+            float ms[5];
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], c->ev_prof[i], c->ev_prof[i + 1]);
+            n.t_kernel[0] += ms[4]; n.t_kernel[1] += ms[1]; n.t_kernel[2] += ms[2]; n.t_kernel[3] += ms[0] + ms[3]; n.t_kernel[4] += 1;
+        }
         c->t_gpu_wait += ms_since(tw);
-        float ems = 0.f;
-        cudaEventElapsedTime(&ems, c->ev0, c->ev1);  // device time of this step's graph replay, on the codec stream
-        c->t_gpu_steps += ems;
-        if (!is_code) c->t_gpu_steps_imp += ems;
         auto th = clk::now();
         const int len = n.steps[p].len;
         rc = is_code ? coder_decode_packed_gmm(coder, c->rows_step_host, len, c->syms_host)
@@ -478,12 +647,14 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code, lic360_coder
         if (rc) return rc;
     }
     // scatter the symbols of the last step (the final TileInput of lic360_demo.py:236,285)
+    const WfNetDev& w = n.wf.dev;
     const int tgrid = (n.max_len + 127) / 128;
     if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W, -3.5f, 1.0f, 3, nullptr);
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
     else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.frame[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W, -1.0f,
-                                                  (float)(2. / (48 - 1.)), 1, c->levels_dev);
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     return LIC360_OK;
 }
@@ -517,7 +688,8 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     rc = decode_stream(c, c->code, true, c->coder[0]);
     if (rc) return rc;
     const int nel = 48 * c->H * c->W;
-    finish_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(c->code.frame[0], c->mask192_dev, code_out_dev, nel, 3.5f);
+    finish_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(c->code.wf.fc[0], c->mask192_dev, code_out_dev, 48, c->H, c->W,
+                                                             c->code.wf.dev.Dp, c->code.wf.dev.Hp, 3.5f);
     LAUNCH_CHECK();
     LIC360_CUDA(cudaStreamSynchronize(s));
     c->t_total = ms_since(t0);
@@ -527,6 +699,19 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n) {
     const double v[6] = {c->t_total, c->t_host_coder, c->t_gpu_wait, c->t_imp, c->t_gpu_steps, c->t_gpu_steps_imp};
     for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
+    return LIC360_OK;
+}
+
+int lic360_codec_set_mode(lic360_codec* c, int mode) {
+    LIC360_CHECK_ARG(c && (mode == 0 || mode == 1), "mode must be 0 (pipelined graph replay) or 1 (serialized, per-kernel timing)");
+    c->mode = mode;
+    return LIC360_OK;
+}
+
+int lic360_codec_kernel_times(lic360_codec* c, int stream_id, double* out, int n) {
+    LIC360_CHECK_ARG(c && out, "bad arguments");
+    const NetDesc& d = stream_id == 0 ? c->code : c->imp;
+    for (int i = 0; i < n && i < 5; i++) out[i] = d.t_kernel[i];
     return LIC360_OK;
 }
 

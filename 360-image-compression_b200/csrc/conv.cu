@@ -1,51 +1,55 @@
 // Masked 3-D context convolution: encode form (CconvEc, whole frame) and wavefront decode form (CconvDc).
 // Replaces /root/reference/extension/cconv_ec_cuda.cu:54-339 and cconv_dc_cuda.cu:58-398.
 //
-// CANONICAL PER-OUTPUT ARITHMETIC (shared by the EC and DC kernels so that encoder and decoder produce
-// bit-identical fp32 values -- the arithmetic decoder desynchronises otherwise, SURVEY.md s7 hard part 1):
+// CANONICAL PER-OUTPUT ARITHMETIC (shared by the EC kernel, the per-op DC kernel and the wavefront engine of the fused
+// decoder, wavefront.cu, so that encoder and decoder produce bit-identical fp32 values -- the arithmetic decoder
+// desynchronises otherwise, SURVEY.md s7 hard part 1).  The terms of one output (h, w, g_out), wavefront p = h+w+g_out,
+// are split by the wavefront q = p - g_out - 4 + kh + kw + g_in of the input they read:
 //
 //   glim(kh,kw) = g_out + 4 - kh - kw                      (mask rule, cconv_ec_cuda.cu:71)
-//   P = 0                                                  "past": input groups g_in <  glim
+//   P = 0                                                  "old": q <= p-2, i.e. input groups g_in <= glim - 2
 //   for j in 0 .. ceil(Cin/16)-1:                          16-channel blocks, ascending
 //       u = 0
 //       for ci in block j (ascending): for kh in 0..4: for kw in 0..4:
-//           if tap inside the image and ci/cin_g < glim:   u = fmaf(x[ci,ph,pw], W[o,ci,kh,kw], u)
+//           if tap inside the image and ci/cin_g <= glim-2: u = fmaf(x[ci,ph,pw], W[o,ci,kh,kw], u)
 //       P = P + u
-//   Q = 0                                                  "present": g_in == glim (constrain 6 only)
+//   R = terms of the previous wavefront  (q == p-1: g_in == glim - 1), Q = terms of the same wavefront (q == p:
+//   g_in == glim, constrain 6 only); both in the same order, with gsel = glim - 1 resp. glim:
 //   for jq in 0 .. ceil(cin_g/16)-1:                       16-channel blocks of the group (one block when cin_g <= 16)
-//     q = 0
+//     r = 0
 //     for c0 in 16*jq, 16*jq+4, ..:                        4-channel chunks of the block
-//       for kh: for kw: if tap inside the image and 0 <= glim < G:
-//         for c in c0 .. min(c0+4, cin_g)-1:               q = fmaf(x[glim*cin_g+c,ph,pw], W[o,glim*cin_g+c,kh,kw], q)
-//     Q = Q + q
-//   out = (P + Q) + bias[o];  PReLU: out > 0 ? out : out*slope[o];  optional residual: out = out + r
+//       for kh: for kw: if tap inside the image and 0 <= gsel < G:
+//         for c in c0 .. min(c0+4, cin_g)-1:               r = fmaf(x[gsel*cin_g+c,ph,pw], W[o,gsel*cin_g+c,kh,kw], r)
+//     R = R + r
+//   out = ((P + R) + Q) + bias[o];  PReLU: out > 0 ? out : out*slope[o];  optional residual: out = out + r
 //
-// Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical bits
-// (fmaf(x, 0, u) == u for finite x).  The past/present split keeps the latency-critical same-wavefront terms
-// (<= 25*cin_g MACs) separable from the bulk, which only needs data of earlier steps.
+// Terms that are skipped in one kernel and multiplied by an exact zero in the other give identical values
+// (fmaf(x, 0, u) == u for finite x).  The three-way split is what makes the decoder pipeline: P of step p+1 only
+// needs data of steps <= p-1 and is computed while step p is still on its critical path (R, then the 12-layer chain
+// of Q terms, <= 25*cin_g MACs each).
 #include <algorithm>
 #include "internal.cuh"
+#include "conv_dev.cuh"
 
 namespace lic360 {
 
-constexpr int CB = 16;    // canonical input-channel block
-constexpr int TAPS = 25;  // 5x5
 constexpr int TH = 8, TW = 32, XH = TH + 4, XW = TW + 4;  // EC spatial tile and its halo'd smem tile
 constexpr int EC_CHUNKS = 8;                              // 8 four-channel output chunks (32 channels) per EC block
 constexpr int EC_THREADS = 256;
 constexpr int EC_SMEM_BYTES = (CB * XH * XW + EC_CHUNKS * CB * TAPS * 4) * (int)sizeof(float);
 
 // ---------------------------------------------------------------------------------------------------------
-// weight packing: W (nsets,Cout,Cin,5,5) -> Wp [set][chunk][ci][tap][4] (past-masked) and
-//                                           Wq [set][chunk][tap][c][4] (present terms)
+// weight packing: W (nsets,Cout,Cin,5,5) -> Wp [set][chunk][ci][tap][4] ("old" terms, everything else zeroed) and
+//                                           Wq [cls][set][chunk][tap][c][4], cls 0 = previous-wavefront terms (R),
+//                                                                          cls 1 = same-wavefront terms (Q)
 // chunk = g_out * cpg4 + (4-channel chunk inside the group); channels beyond cout_g are zero padding.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wq,
                                   int nsets, int Cin, int Cout, int G, int constrain) {
     const int cin_g = Cin / G, cout_g = Cout / G, cpg4 = (cout_g + 3) / 4, nchunk = G * cpg4;
     const size_t np = (size_t)nsets * nchunk * Cin * TAPS * 4;
-    const size_t nq = (size_t)nsets * nchunk * TAPS * cin_g * 4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + nq; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t nq = (size_t)nsets * nchunk * TAPS * cin_g * 4;  // per class
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + 2 * nq; i += (size_t)gridDim.x * blockDim.x) {
         if (i < np) {
             int q = i % 4;
             int tap = (i / 4) % TAPS;
@@ -55,22 +59,23 @@ __global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict
             int g_out = chunk / cpg4, oc = (chunk % cpg4) * 4 + q;
             int glim = g_out + 4 - tap / 5 - tap % 5;
             float v = 0.f;
-            if (oc < cout_g && ci / cin_g < glim)
+            if (oc < cout_g && ci / cin_g <= glim - 2)
                 v = w[(((size_t)set * Cout + g_out * cout_g + oc) * Cin + ci) * TAPS + tap];
             wp[i] = v;
         } else {
-            size_t k = i - np;
+            const int cls = (i - np) >= nq;
+            size_t k = i - np - (cls ? nq : 0);
             int q = k % 4;
             int c = (k / 4) % cin_g;
             int tap = (k / ((size_t)4 * cin_g)) % TAPS;
             int chunk = (k / ((size_t)4 * cin_g * TAPS)) % nchunk;
             int set = k / ((size_t)4 * cin_g * TAPS * nchunk);
             int g_out = chunk / cpg4, oc = (chunk % cpg4) * 4 + q;
-            int glim = g_out + 4 - tap / 5 - tap % 5;
+            int gsel = g_out + 3 + cls - tap / 5 - tap % 5;
             float v = 0.f;
-            if (oc < cout_g && constrain == 6 && glim >= 0 && glim < G)
-                v = w[(((size_t)set * Cout + g_out * cout_g + oc) * Cin + glim * cin_g + c) * TAPS + tap];
-            wq[k] = v;
+            if (oc < cout_g && (cls == 0 || constrain == 6) && gsel >= 0 && gsel < G)
+                v = w[(((size_t)set * Cout + g_out * cout_g + oc) * Cin + gsel * cin_g + c) * TAPS + tap];
+            wq[i - np] = v;
         }
     }
 }
@@ -96,10 +101,10 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
     const int Cin = a.Cin, H = a.H, W = a.W;
 
     const int last_chunk = min(chunk0 + EC_CHUNKS - 1, a.nchunk - 1);
-    const int lim_tile = min(Cin, (last_chunk / a.cpg4 + 4) * a.cin_g);
+    const int lim_tile = min(Cin, (last_chunk / a.cpg4 + 3) * a.cin_g);  // old terms: g_in <= g_out + 2
     const int nj = (lim_tile + CB - 1) / CB;
     const int cA = chunk0 + 2 * tz;
-    const int my_lim = min(Cin, (min(cA + 1, a.nchunk - 1) / a.cpg4 + 4) * a.cin_g);
+    const int my_lim = min(Cin, (min(cA + 1, a.nchunk - 1) / a.cpg4 + 3) * a.cin_g);
 
     float P[2][4][4];
 #pragma unroll
@@ -173,20 +178,23 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
         __syncthreads();
     }
 
-    // present terms + epilogue
+    // previous-wavefront (R) and same-wavefront (Q) terms + epilogue
     const int h = h0 + ty;
     const float4* wq4 = reinterpret_cast<const float4*>(a.wq);
+    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * TAPS * a.cin_g;  // float4 per class
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
         const int chunk = cA + cc;
         if (chunk >= a.nchunk || h >= H) continue;
         const int g_out = chunk / a.cpg4;
-        float Q[4][4];
+        float RQ[2][4][4];
 #pragma unroll
-        for (int p = 0; p < 4; p++)
+        for (int cls = 0; cls < 2; cls++) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) Q[p][q] = 0.f;
-        if (a.has_q) {
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) RQ[cls][p][q] = 0.f;
+            if (cls == 1 && !a.has_q) continue;
             for (int jq = 0; jq * CB < a.cin_g; jq++) {
                 float qq[4][4];
 #pragma unroll
@@ -200,9 +208,9 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
                         const int ph = h + kh - 2;
                         if (ph < 0 || ph >= H) continue;
                         for (int kw = 0; kw < 5; kw++) {
-                            const int gq = g_out + 4 - kh - kw;
+                            const int gq = g_out + 3 + cls - kh - kw;
                             if (gq < 0 || gq >= a.G) continue;
-                            const float4* wrow = wq4 + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
+                            const float4* wrow = wq4 + cls * wq_cls + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
                             const float* xrow = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W;
                             for (int c = c0; c < c1; c++) {
                                 const float4 w4 = __ldg(wrow + c);
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 #pragma unroll
                 for (int p = 0; p < 4; p++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) Q[p][q] = Q[p][q] + qq[p][q];
+                    for (int q = 0; q < 4; q++) RQ[cls][p][q] = RQ[cls][p][q] + qq[p][q];
             }
         }
 #pragma unroll
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
             for (int p = 0; p < 4; p++) {
                 const int w = w0 + 4 * tx + p;
                 if (w >= W) continue;
-                float v = (P[cc][p][q] + Q[p][q]) + b;
+                float v = ((P[cc][p][q] + RQ[0][p][q]) + RQ[1][p][q]) + b;
                 if (a.slope) v = v > 0.f ? v : v * sl;
                 if (a.resid) v = v + a.resid[row + w];
                 a.out[row + w] = v;
@@ -258,49 +266,40 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 // lane walks its window from shared memory (stride-9 rows: bank-conflict free) against warp-uniform float4 weight
 // loads.  Segment partials meet in shared memory and are combined in the canonical order by warp 0.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int DC_BAND = 36 * 9;          // cells per channel
-constexpr int DC_STAGE = 4;              // channels staged per round
-constexpr int DC_WARP_FLOATS = DC_STAGE * DC_BAND + DC_STAGE * TAPS * 4;  // band + weights of one stage
-
-__device__ __forceinline__ void cp_async4(unsigned dst, const void* src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0));
-}
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
-// 100 taps of one stage out of shared memory: x from the band (row stride 9: conflict free), weights broadcast
-// bound0/cin_g: taps with kh + kw >= tc + 4 - group(channel) carry a zero weight and are skipped (warp-uniform)
-__device__ __forceinline__ void dc_stage_fma(const float* band, const float4* wsm, int nc, int lane, int chan0, int cin_g,
-                                             int tc, float4& u) {
-    for (int ch = 0; ch < nc; ch++) {
-        const float* bw = band + ch * DC_BAND + lane * 9;
-        const float4* wrow = wsm + ch * TAPS;
-        const int bound = tc + 4 - (chan0 + ch) / cin_g;
+// canonical combine of the segment partials + bias / PReLU / residual; p = element offset of channel 0 of this
+// position in the output frame, cstride = channel stride of that frame
+__device__ __forceinline__ void dc_combine_store(const ConvArgs& a, const float4* part, int nblk, int nqb, int lane, int tc,
+                                                 int set, int ochunk, size_t p0, size_t cstride) {
+    float P[4] = {0.f, 0.f, 0.f, 0.f}, R[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < nblk; j++) {
+        const float4 v = part[j * 32 + lane];
+        P[0] = P[0] + v.x; P[1] = P[1] + v.y; P[2] = P[2] + v.z; P[3] = P[3] + v.w;
+    }
+    for (int j = nblk; j < nblk + nqb; j++) {
+        const float4 v = part[j * 32 + lane];
+        R[0] = R[0] + v.x; R[1] = R[1] + v.y; R[2] = R[2] + v.z; R[3] = R[3] + v.w;
+    }
+    for (int j = nblk + nqb; j < nblk + 2 * nqb; j++) {  // zero partials when !has_q
+        const float4 v = part[j * 32 + lane];
+        Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
+    }
 #pragma unroll
-        for (int kh = 0; kh < 5; kh++) {
-#pragma unroll
-            for (int kw = 0; kw < 5; kw++) {
-                if (kh + kw >= bound) continue;
-                const float xx = bw[kh * 9 + kh + kw];
-                const float4 w4 = wrow[kh * 5 + kw];
-                u.x = fmaf(xx, w4.x, u.x);
-                u.y = fmaf(xx, w4.y, u.y);
-                u.z = fmaf(xx, w4.z, u.z);
-                u.w = fmaf(xx, w4.w, u.w);
-            }
-        }
+    for (int q = 0; q < 4; q++) {
+        const int oc = ochunk * 4 + q;
+        if (oc >= a.cout_g) continue;
+        const int o = tc * a.cout_g + oc;
+        float v = ((P[q] + R[q]) + Q[q]) + __ldg(a.bias + set * a.Cout + o);
+        if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
+        const size_t p = p0 + (size_t)o * cstride;
+        if (a.resid) v = v + a.resid[p];
+        a.out[p] = v;
     }
 }
 
 __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int psum, int nblk, int nqb, int parts,
                                                       const StepDesc* __restrict__ steps, const int* __restrict__ ctr) {
     extern __shared__ float4 dc_smem4[];
-    const int nseg = nblk + nqb;                                           // past segments then present segments
+    const int nseg = nblk + 2 * nqb;                                       // old segments, then R, then Q segments
     float4* part = dc_smem4;                                               // [nseg][32]
     int* boff = reinterpret_cast<int*>(dc_smem4 + nseg * 32);              // [DC_BAND] band cell -> row*W+col or -1
     float* stage_all = reinterpret_cast<float*>(boff + DC_BAND);           // [nseg][DC_WARP_FLOATS]
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
     const unsigned wsm_s = (unsigned)__cvta_generic_to_shared(wsm);
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
     if (seg < nblk) {
-        const int lim = min(Cin, (tc + 4) * a.cin_g);
+        const int lim = min(Cin, (tc + 3) * a.cin_g);  // old terms: g_in <= tc + 2
         if (seg * CB < lim) {
             const int cb = min(CB, Cin - seg * CB);
             const float4* wp4 = reinterpret_cast<const float4*>(a.wp) + (((size_t)set * a.nchunk + chunk) * Cin + seg * CB) * TAPS;
@@ -350,15 +349,18 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
                 for (int e = lane; e < nc * TAPS; e += 32) cp_async16(wsm_s + 16u * e, wp4 + c0 * TAPS + e);
                 cp_async_wait_all();
                 __syncwarp();
-                dc_stage_fma(band, wsm, nc, lane, seg * CB + c0, a.cin_g, tc, u);
+                dc_stage_fma<9, 1, DC_BAND>(band, wsm, nc, lane, seg * CB + c0, a.cin_g, tc, u);
             }
         }
-    } else if (a.has_q) {
-        // present terms, 16-channel block jq of the group: tap (kh,kw) reads group gq = tc + 4 - (kh+kw) at band column
-        // cc = kh+kw, so the stage holds, for every column cc, the 4-channel chunk [c0, c0+4) of group tc + 4 - cc
-        const int jq = seg - nblk;
+    } else if (seg < nblk + nqb || a.has_q) {
+        // R (cls 0) / Q (cls 1) terms, 16-channel block jq of the group: tap (kh,kw) reads group gq = tc + 3 + cls - (kh+kw)
+        // at band column cc = kh+kw, so the stage holds, for every column cc, the 4-channel chunk [c0, c0+4) of that group
+        const int cls = seg >= nblk + nqb;
+        const int jq = seg - nblk - cls * nqb;
+        const int gsel0 = tc + 3 + cls;
         const int cend = min((jq + 1) * CB, a.cin_g);
-        const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * TAPS * a.cin_g;
+        const float4* wq4 = reinterpret_cast<const float4*>(a.wq) +
+                            ((size_t)(cls * (a.N / a.per) + set) * a.nchunk + chunk) * TAPS * a.cin_g;
         const float* xn = a.x + (size_t)n * Cin * HW;
         for (int c0 = jq * CB; c0 < cend; c0 += DC_STAGE) {
             const int nc = min(DC_STAGE, cend - c0);
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
 #pragma unroll 4
                 for (int r = lane; r < DC_BAND; r += 32) {
                     const int off = boff[r];
-                    const int gq = tc + 4 - r % 9;
+                    const int gq = gsel0 - r % 9;
                     const bool ok = off >= 0 && gq >= 0 && gq < a.G;
                     cp_async4(band_s + 4u * (ch * DC_BAND + r), ok ? xn + (size_t)(gq * a.cin_g + c0 + ch) * HW + off : xn, ok);
                 }
@@ -376,50 +378,13 @@ __global__ void __launch_bounds__(1024) cconv_dc_kernel(const ConvArgs a, int ps
             for (int e = lane; e < nc * TAPS; e += 32) cp_async16(wsm_s + 16u * e, wq4 + (e % TAPS) * a.cin_g + c0 + e / TAPS);
             cp_async_wait_all();
             __syncwarp();
-            // canonical order inside the chunk is (kh, kw, c): channel innermost
-#pragma unroll
-            for (int kh = 0; kh < 5; kh++) {
-#pragma unroll
-                for (int kw = 0; kw < 5; kw++) {
-                    const int gq = tc + 4 - kh - kw;
-                    if (gq < 0 || gq >= a.G) continue;  // warp-uniform
-                    for (int ch = 0; ch < nc; ch++) {
-                        const float xx = band[ch * DC_BAND + (lane + kh) * 9 + kh + kw];
-                        const float4 w4 = wsm[ch * TAPS + kh * 5 + kw];
-                        u.x = fmaf(xx, w4.x, u.x);
-                        u.y = fmaf(xx, w4.y, u.y);
-                        u.z = fmaf(xx, w4.z, u.z);
-                        u.w = fmaf(xx, w4.w, u.w);
-                    }
-                }
-            }
+            dc_stage_q<9, 1, DC_BAND>(band, wsm, nc, lane, gsel0, a.G, u);
         }
     }
     part[seg * 32 + lane] = u;
     __syncthreads();
-    if (seg == 0 && valid) {
-        float P[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < nblk; j++) {
-            const float4 v = part[j * 32 + lane];
-            P[0] = P[0] + v.x; P[1] = P[1] + v.y; P[2] = P[2] + v.z; P[3] = P[3] + v.w;
-        }
-        float Q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = nblk; j < nseg; j++) {  // zero partials when !has_q
-            const float4 v = part[j * 32 + lane];
-            Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int oc = blockIdx.y * 4 + q;
-            if (oc >= a.cout_g) continue;
-            const int o = tc * a.cout_g + oc;
-            float v = (P[q] + Q[q]) + __ldg(a.bias + set * a.Cout + o);
-            if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
-            const size_t p = (((size_t)n * a.Cout + o) * H + th) * W + tw;
-            if (a.resid) v = v + a.resid[p];
-            a.out[p] = v;
-        }
-    }
+    if (seg == 0 && valid)
+        dc_combine_store(a, part, nblk, nqb, lane, tc, set, blockIdx.y, ((size_t)n * a.Cout * H + th) * W + tw, (size_t)HW);
 }
 
 int fill_conv_args(ConvArgs& a, const float* x, const float* wp, const float* wq, const float* bias,
@@ -455,8 +420,8 @@ cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start
     if (!steps && len <= 0) return cudaSuccess;
     const int parts = (std::min(a.H, a.W) + 31) / 32;          // 32-position chunks per anti-diagonal
     const int ndiag = std::min(a.G, a.H + a.W - 1);            // a slab holds at most G diagonals
-    const int nqb = a.has_q ? (a.cin_g + CB - 1) / CB : 1;
-    const int nseg = nblk + nqb;
+    const int nqb = (a.cin_g + CB - 1) / CB;
+    const int nseg = nblk + 2 * nqb;
     if (nseg > 32) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)nseg * 32 * sizeof(float4) + DC_BAND * sizeof(int) + (size_t)nseg * DC_WARP_FLOATS * sizeof(float);
     static size_t attr_smem = 0;
@@ -481,7 +446,7 @@ extern "C" size_t lic360_cconv_wp_floats(int nsets, int Cin, int Cout, int G) {
 }
 extern "C" size_t lic360_cconv_wq_floats(int nsets, int Cin, int Cout, int G) {
     int cpg4 = (Cout / G + 3) / 4;
-    return (size_t)nsets * G * cpg4 * TAPS * (Cin / G) * 4;
+    return (size_t)2 * nsets * G * cpg4 * TAPS * (Cin / G) * 4;  // two classes: previous-wavefront and same-wavefront terms
 }
 
 extern "C" int lic360_cconv_pack(const float* w_dev, float* wp_dev, float* wq_dev, int nsets, int Cin, int Cout, int G,
@@ -515,7 +480,7 @@ extern "C" int lic360_cconv_dc_forward(const float* x_dev, const float* wp_dev, 
     LIC360_CHECK_ARG(fill_conv_args(a, x_dev, wp_dev, wq_dev, bias_dev, slope_dev, resid_dev, out_dev, N, Cin, H, W, Cout, G,
                                constrain, nsets) == 0, "bad shape / constrain");
     const int nblk = (Cin + CB - 1) / CB;
-    LIC360_CHECK_ARG(nblk + (Cin / G + CB - 1) / CB <= 32, "Cin too large for the wavefront kernel");
+    LIC360_CHECK_ARG(nblk + 2 * ((Cin / G + CB - 1) / CB) <= 32, "Cin too large for the wavefront kernel");
     const int mod = H + W + G - 2;
     int start, len;
     slab_of(plan_host, H, W, G, psum, &start, &len);

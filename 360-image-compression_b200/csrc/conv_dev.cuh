@@ -1,0 +1,76 @@
+// Device helpers shared by the per-op context-conv kernels (conv.cu) and the wavefront engine of the fused decoder
+// (wavefront.cu): one definition of the canonical per-stage arithmetic (see the header of conv.cu), so that every
+// kernel that produces a context-conv output produces the same bits.
+#pragma once
+#include "common.cuh"
+
+namespace lic360 {
+
+constexpr int CB = 16;    // canonical input-channel block
+constexpr int TAPS = 25;  // 5x5
+constexpr int DC_BAND = 36 * 9;          // cells per channel
+constexpr int DC_STAGE = 4;              // channels staged per round
+constexpr int DC_WARP_FLOATS = DC_STAGE * DC_BAND + DC_STAGE * TAPS * 4;  // band + weights of one stage
+
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0));
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// 100 taps of one stage out of shared memory: x from the band (row stride 9: conflict free), weights broadcast
+// old terms only: taps with kh + kw >= tc + 3 - group(channel) carry a zero weight and are skipped (warp-uniform)
+// band cell of position `lane`, tap (kh,kw): band[ch*DC_BAND + (lane+kh)*RS + (kh+kw)*CS]
+//   NCHW kernel  : rows = image rows, 9 columns         -> RS = 9, CS = 1,  CHS = 324
+//   skewed kernel: rows = diagonals (kh+kw), 40 columns -> RS = 1, CS = 40, CHS = 360 (TMA box, wavefront.cu)
+template <int RS, int CS, int CHS>
+__device__ __forceinline__ void dc_stage_fma(const float* band, const float4* wsm, int nc, int lane, int chan0, int cin_g,
+                                             int tc, float4& u) {
+    for (int ch = 0; ch < nc; ch++) {
+        const float* bw = band + ch * CHS + lane * RS;
+        const float4* wrow = wsm + ch * TAPS;
+        const int bound = tc + 3 - (chan0 + ch) / cin_g;
+#pragma unroll
+        for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+            for (int kw = 0; kw < 5; kw++) {
+                if (kh + kw >= bound) continue;
+                const float xx = bw[kh * RS + (kh + kw) * CS];
+                const float4 w4 = wrow[kh * 5 + kw];
+                u.x = fmaf(xx, w4.x, u.x);
+                u.y = fmaf(xx, w4.y, u.y);
+                u.z = fmaf(xx, w4.z, u.z);
+                u.w = fmaf(xx, w4.w, u.w);
+            }
+        }
+    }
+}
+
+// previous- (gsel0 = tc + 3) or same-wavefront (gsel0 = tc + 4) taps of one 4-channel chunk: canonical order (kh, kw, c)
+template <int RS, int CS, int CHS>
+__device__ __forceinline__ void dc_stage_q(const float* band, const float4* wsm, int nc, int lane, int gsel0, int G, float4& u) {
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            const int gq = gsel0 - kh - kw;
+            if (gq < 0 || gq >= G) continue;  // warp-uniform
+            for (int ch = 0; ch < nc; ch++) {
+                const float xx = band[ch * CHS + (lane + kh) * RS + (kh + kw) * CS];
+                const float4 w4 = wsm[ch * TAPS + kh * 5 + kw];
+                u.x = fmaf(xx, w4.x, u.x);
+                u.y = fmaf(xx, w4.y, u.y);
+                u.z = fmaf(xx, w4.z, u.z);
+                u.w = fmaf(xx, w4.w, u.w);
+            }
+        }
+    }
+}
+
+
+}  // namespace lic360

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared between the op entry points and the fused codec pipeline.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace lic360 {

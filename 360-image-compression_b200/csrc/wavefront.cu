@@ -1,0 +1,536 @@
+// Wavefront engine of the fused decoder.  Replaces the 12 CconvDc launches (+5 TileAdd) that the reference issues per
+// wavefront step (test/lic360_demo.py:201-209,226-234; cconv_dc_cuda.cu:108-137; tile_add_cuda.cu:40-61).
+//
+// A decoder step p is strictly sequential across layers only through the SAME-wavefront terms (Q) of each layer, at
+// most 25*cin_g MACs per output.  The canonical arithmetic (conv.cu header) therefore splits every output into
+//     out = ((P + R) + Q) + bias
+//   P : "old" terms, inputs of wavefronts <= p-2       -> wf_old_kernel : ALL 12 layers in one launch, fed by TMA box
+//                                                         loads; launched for step p+1 on a side branch of step p's
+//                                                         graph, i.e. off the critical path (it only needs data that is
+//                                                         complete before step p starts)
+//   R : inputs of wavefront p-1 (available at step start) -> wf_prev_kernel: all 12 layers in one launch
+//   Q : inputs of wavefront p (the layer below, this step) -> wf_chain_kernel: one thread-block cluster per net walks
+//                                                         the 12 layers with a cluster barrier between layers; bias,
+//                                                         PReLU and the residual add (TileAdd) are fused here
+// so the critical path of a step is  scatter -> R -> chain -> CDF rows  instead of 12 dependent full-size launches.
+#include <algorithm>
+#include <cooperative_groups.h>
+#include <vector>
+#include "conv_dev.cuh"
+#include "wavefront.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lic360 {
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier
+// The inner (h) coordinate of a TMA box must be 16-byte aligned (4 floats; an unaligned start faults with "illegal
+// instruction" on sm_100, tools/tma_probe.cu), so the box starts at (hbase - 2) rounded down to 4 and is 40 wide.
+constexpr int WF_BOX_W = 40;
+constexpr int WF_BAND = 9 * WF_BOX_W;                 // cells per channel
+constexpr int WF_BAND_BYTES = DC_STAGE * WF_BAND * 4;  // 5760
+constexpr int WF_STAGE_BYTES = 7424;                  // band + 4 x 25 float4 weights (1600 B), padded to a multiple of 128
+
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, int bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// CTA geometry shared by the old-term and previous-wavefront kernels:
+//   blockIdx.x -> (diagonal of the slab, 32-position part), blockIdx.y -> 4-channel output chunk inside the group,
+//   blockIdx.z -> (layer, net)
+struct WfTile { int l, n, kc, psum, d, hbase, hmax, tc; bool ok; };
+
+__device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp) {
+    WfTile t;
+    t.l = blockIdx.z / net.nsets;
+    t.n = blockIdx.z % net.nsets;
+    t.kc = blockIdx.y;
+    t.psum = *net.ctr + dp;
+    t.ok = t.kc < net.L[t.l].cpg4 && t.psum < net.nsteps;
+    const int la = max(0, t.psum - net.G + 1), lb = min(t.psum, net.H + net.W - 2);
+    t.d = la + blockIdx.x / net.parts;
+    t.ok = t.ok && t.d <= lb;
+    const int hmin = max(0, t.d - net.W + 1);
+    t.hmax = min(net.H - 1, t.d);
+    t.hbase = hmin + (blockIdx.x % net.parts) * 32;
+    t.ok = t.ok && t.hbase <= t.hmax;
+    t.tc = t.psum - t.d;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------ old terms (P)
+// CTA = 32 consecutive positions of one anti-diagonal x one 4-channel output chunk x (layer, net); warp j = canonical
+// 16-channel input block j.  Per stage of 4 input channels ONE 3-D TMA box {36 h, 9 d, 4 c} of the planar skewed frame
+// (out-of-image cells zero-filled by the TMA unit: no index math, no bounds checks) plus one bulk copy of the stage's
+// 100 float4 weights land in the warp's private shared-memory slice and complete on the warp's own mbarrier.
+__global__ void __launch_bounds__(1024) wf_old_kernel(const __grid_constant__ WfNetDev net, const __grid_constant__ WfMaps maps,
+                                                    int dp) {
+    extern __shared__ unsigned char wf_raw[];
+    const WfTile t = wf_tile(net, dp);
+    if (!t.ok) return;  // CTA-uniform
+    const WfLayerDev& L = net.L[t.l];
+    const int nseg = blockDim.y;
+    const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
+    unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                     // 128-B aligned
+    float4* part = reinterpret_cast<float4*>(base + (size_t)nseg * WF_STAGE_BYTES);      // [nseg][32]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + nseg * 32);  // [nseg]
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    float* band = reinterpret_cast<float*>(base + (size_t)seg * WF_STAGE_BYTES);
+    float4* wsm = reinterpret_cast<float4*>(band + DC_STAGE * WF_BAND);
+    const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
+    const unsigned wsm_s = band_s + WF_BAND_BYTES;
+    const int h0 = (t.hbase - 2) & ~3;   // aligned box start (also for negative values: two's complement floor)
+    const float* bandl = band + (t.hbase - 2 - h0);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + seg);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (seg < L.nblk) {
+        const int Cin = L.Cin;
+        const int lim = min(Cin, (t.tc + 3) * L.cin_g);  // old terms: g_in <= tc + 2
+        const int cb = min(CB, Cin - seg * CB);
+        const int chunk = t.tc * L.cpg4 + t.kc;
+        const float4* wp4 = reinterpret_cast<const float4*>(L.wp) + (((size_t)t.n * L.nchunk + chunk) * Cin + seg * CB) * TAPS;
+        unsigned phase = 0;
+        for (int c0 = 0; c0 < cb && seg * CB + c0 < lim; c0 += DC_STAGE) {
+            const int nc = min(DC_STAGE, cb - c0);
+            __syncwarp();  // every lane is done with the previous stage
+            if (lane == 0) {
+                mbar_expect_tx(bar, WF_BAND_BYTES + nc * TAPS * 16);
+                tma_load_3d(band_s, &maps.tm[t.l], h0, t.d - 4, t.n * Cin + seg * CB + c0, bar);
+                bulk_load(wsm_s, wp4 + c0 * TAPS, nc * TAPS * 16, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            dc_stage_fma<1, WF_BOX_W, WF_BAND>(bandl, wsm, nc, lane, seg * CB + c0, L.cin_g, t.tc, u);
+        }
+    }
+    part[seg * 32 + lane] = u;
+    __syncthreads();
+    const int h = t.hbase + lane;
+    if (seg == 0 && h <= t.hmax) {
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < L.nblk; j++) {
+            const float4 v = part[j * 32 + lane];
+            P.x = P.x + v.x; P.y = P.y + v.y; P.z = P.z + v.z; P.w = P.w + v.w;
+        }
+        L.pbuf[t.psum & 1][(((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h] = P;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ R / Q terms
+// one canonical 16-channel block (jq) of the previous-wavefront (cls 0) or same-wavefront (cls 1) terms of output
+// (d, h, group tc, chunk kc): every tap reads the cin_g channels of ONE input group from the channel-last frame.
+// CG: read with ld.global.cg (the chain kernel consumes values produced by other CTAs of its cluster in the same launch).
+template <bool CG>
+__device__ __forceinline__ float4 wf_ldx4(const float* p) {
+    return CG ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// The activation and weight loads of a whole kernel row (5 taps x 4 channels) are issued before the row's first FMA:
+// these kernels run few warps per SM right after a cluster barrier (cold L1), so one L2 round trip per row instead of one
+// per weight vector is the difference between ~1 us and ~15 us per layer.  The FMA order is the canonical one.
+template <bool CG>
+__device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLayerDev& L, int n, int d, int h, int tc, int kc,
+                                                int jq, int cls) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cin_g = L.cin_g, C = L.Cin;
+    const int gsel0 = tc + 3 + cls;
+    const int cend = min((jq + 1) * CB, cin_g);
+    const float4* w = reinterpret_cast<const float4*>(L.wq) +
+                      ((size_t)(cls * net.nsets + n) * L.nchunk + tc * L.cpg4 + kc) * TAPS * cin_g;
+    // cell (d-4+kh+kw, h-2+kh) of the padded channel-last frame = xb + ((kh+kw) * Hp + kh) * C
+    const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.Hp + h) * C;
+    const int Hp = net.Hp;
+    if ((cin_g & 3) == 0 && net.G == 1) {
+        // one group: input group 0 is selected by exactly the taps with kh + kw == gsel0 (3 or 4)
+        for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+            float4 xv[5], wv[5][4];
+#pragma unroll
+            for (int kh = 0; kh < 5; kh++) {
+                const int kw = gsel0 - kh;
+                const bool ok = kw >= 0 && kw < 5;
+                xv[kh] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) xv[kh] = wf_ldx4<CG>(xb + ((size_t)gsel0 * Hp + kh) * C + c0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    wv[kh][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) wv[kh][c] = __ldg(w + (kh * 5 + kw) * cin_g + c0 + c);
+                }
+            }
+#pragma unroll
+            for (int kh = 0; kh < 5; kh++) {
+                const int kw = gsel0 - kh;
+                if (kw < 0 || kw >= 5) continue;
+                const float xs[4] = {xv[kh].x, xv[kh].y, xv[kh].z, xv[kh].w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    u.x = fmaf(xs[c], wv[kh][c].x, u.x);
+                    u.y = fmaf(xs[c], wv[kh][c].y, u.y);
+                    u.z = fmaf(xs[c], wv[kh][c].z, u.z);
+                    u.w = fmaf(xs[c], wv[kh][c].w, u.w);
+                }
+            }
+        }
+    } else if ((cin_g & 3) == 0) {
+        // row by row: the 5 activations and 20 weight vectors of a kernel row are in flight together
+        for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+#pragma unroll
+            for (int kh = 0; kh < 5; kh++) {
+                float4 xv[5], wv[5][4];
+#pragma unroll
+                for (int kw = 0; kw < 5; kw++) {
+                    const int gq = gsel0 - kh - kw;
+                    const bool ok = gq >= 0 && gq < net.G;
+                    xv[kw] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) xv[kw] = wf_ldx4<CG>(xb + ((size_t)(kh + kw) * Hp + kh) * C + gq * cin_g + c0);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        wv[kw][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) wv[kw][c] = __ldg(w + (kh * 5 + kw) * cin_g + c0 + c);
+                    }
+                }
+#pragma unroll
+                for (int kw = 0; kw < 5; kw++) {
+                    const int gq = gsel0 - kh - kw;
+                    if (gq < 0 || gq >= net.G) continue;
+                    const float xs[4] = {xv[kw].x, xv[kw].y, xv[kw].z, xv[kw].w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        u.x = fmaf(xs[c], wv[kw][c].x, u.x);
+                        u.y = fmaf(xs[c], wv[kw][c].y, u.y);
+                        u.z = fmaf(xs[c], wv[kw][c].z, u.z);
+                        u.w = fmaf(xs[c], wv[kw][c].w, u.w);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+            const int nc = min(4, cend - c0);
+#pragma unroll
+            for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+                for (int kw = 0; kw < 5; kw++) {
+                    const int gq = gsel0 - kh - kw;
+                    if (gq < 0 || gq >= net.G) continue;
+                    const float* xp = xb + ((size_t)(kh + kw) * Hp + kh) * C + gq * cin_g + c0;
+                    const float4* wt = w + (kh * 5 + kw) * cin_g + c0;
+                    for (int c = 0; c < nc; c++) {
+                        const float xx = CG ? __ldcg(xp + c) : __ldg(xp + c);
+                        const float4 w4 = __ldg(wt + c);
+                        u.x = fmaf(xx, w4.x, u.x);
+                        u.y = fmaf(xx, w4.y, u.y);
+                        u.z = fmaf(xx, w4.z, u.z);
+                        u.w = fmaf(xx, w4.w, u.w);
+                    }
+                }
+            }
+        }
+    }
+    return u;
+}
+
+// previous-wavefront terms of ALL layers of step *ctr: pbuf <- P + R.  Same CTA geometry as wf_old_kernel; warp jq =
+// canonical 16-channel block jq of the group.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant__ WfNetDev net) {
+    extern __shared__ float4 wf_part[];
+    const WfTile t = wf_tile(net, 0);
+    if (!t.ok) return;
+    const WfLayerDev& L = net.L[t.l];
+    const int lane = threadIdx.x, jq = threadIdx.y;
+    const int h = t.hbase + lane;
+    const bool valid = h <= t.hmax;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (jq < L.nqb && valid) r = wf_rq_partial<false>(net, L, t.n, t.d, h, t.tc, t.kc, jq, 0);
+    if (blockDim.y > 1) {
+        wf_part[jq * 32 + lane] = r;
+        __syncthreads();
+        if (jq != 0) return;
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < L.nqb; j++) {
+            const float4 v = wf_part[j * 32 + lane];
+            r.x = r.x + v.x; r.y = r.y + v.y; r.z = r.z + v.z; r.w = r.w + v.w;
+        }
+    } else {
+        r.x = 0.f + r.x; r.y = 0.f + r.y; r.z = 0.f + r.z; r.w = 0.f + r.w;  // R = 0 + r_0, as everywhere else
+    }
+    if (!valid) return;
+    float4* pp = L.pbuf[t.psum & 1] + (((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h;
+    float4 P = *pp;
+    P.x = P.x + r.x; P.y = P.y + r.y; P.z = P.z + r.z; P.w = P.w + r.w;
+    *pp = P;
+}
+
+// ------------------------------------------------------------------------------------------------ the 12-layer chain
+// One thread-block cluster per net.  Layer l: every (slab position, output chunk) item adds its same-wavefront terms
+// (read from the layer below through L2) to P + R, applies bias / PReLU / residual and stores the 4 channels into both
+// frame layouts; a cluster barrier (release / acquire) orders layer l's stores before layer l+1's loads.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant__ WfNetDev net, int nc) {
+    extern __shared__ float4 wf_part[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    const StepDesc sd = net.steps[*net.ctr];
+    const int HW = net.H * net.W;
+    for (int l = 0; l < WF_LAYERS; l++) {
+        const WfLayerDev& L = net.L[l];
+        const int items = sd.len * L.cpg4;
+        const int per = (items + nc - 1) / nc;
+        const int i0 = min(items, rank * per), i1 = min(items, i0 + per), nloc = i1 - i0;
+        const bool direct = L.nqb == 1;  // one canonical block per item: no exchange of partials through shared memory
+        if (L.has_q && !direct) {
+            for (int tsk = tid; tsk < nloc * L.nqb; tsk += nt) {
+                const int jq = tsk / nloc, i = i0 + tsk % nloc;
+                const int kc = i / sd.len, k = sd.start + i % sd.len;
+                const int h = __ldg(net.idx + k), w = __ldg(net.idx + k + HW);
+                wf_part[tsk] = wf_rq_partial<true>(net, L, n, h + w, h, sd.psum - h - w, kc, jq, 1);
+            }
+            __syncthreads();
+        }
+        for (int il = tid; il < nloc; il += nt) {
+            const int i = i0 + il;
+            const int kc = i / sd.len, k = sd.start + i % sd.len;
+            const int h = __ldg(net.idx + k), w = __ldg(net.idx + k + HW);
+            const int d = h + w, tc = sd.psum - d;
+            // independent loads first: P + R, bias, slope, residual
+            const float4 pr = __ldg(L.pbuf[sd.psum & 1] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+            const size_t fc = wf_fc_index(net.Dp, net.Hp, L.Cout, n, d, h) + tc * L.cout_g + kc * 4;
+            const int o0 = tc * L.cout_g + kc * 4;
+            float bs[4], sl[4], rs[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool live = kc * 4 + q < L.cout_g;
+                bs[q] = live ? __ldg(L.bias + n * L.Cout + o0 + q) : 0.f;
+                sl[q] = live && L.slope ? __ldg(L.slope + n * L.Cout + o0 + q) : 0.f;
+                rs[q] = live && L.rc ? __ldcg(L.rc + fc + q) : 0.f;
+            }
+            float Q[4] = {0.f, 0.f, 0.f, 0.f};
+            if (L.has_q) {
+                if (direct) {
+                    const float4 v = wf_rq_partial<true>(net, L, n, d, h, tc, kc, 0, 1);
+                    Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
+                } else {
+                    for (int j = 0; j < L.nqb; j++) {
+                        const float4 v = wf_part[j * nloc + il];
+                        Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
+                    }
+                }
+            }
+            const float PR[4] = {pr.x, pr.y, pr.z, pr.w};
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q] = 0.f;
+                if (kc * 4 + q >= L.cout_g) continue;
+                float y = (PR[q] + Q[q]) + bs[q];
+                if (L.slope) y = y > 0.f ? y : y * sl[q];
+                if (L.rc) y = y + rs[q];
+                v[q] = y;
+                if (L.op) L.op[wf_fp_index(net.D, net.HS, L.Cout, n, o0 + q, d, h)] = y;
+            }
+            if ((L.cout_g & 3) == 0) {
+                *reinterpret_cast<float4*>(L.oc + fc) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (kc * 4 + q < L.cout_g) L.oc[fc + q] = v[q];
+            }
+        }
+        if (l + 1 < WF_LAYERS) {
+            if (nc > 1) cg::this_cluster().sync();
+            else __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, const int32_t* idx_dev, const StepDesc* steps_dev,
+            const int* ctr_dev, int nsteps, int max_len) {
+    WfNetDev& n = e.dev;
+    memset(&n, 0, sizeof(n));
+    n.nsets = nsets; n.G = G; n.H = H; n.W = W; n.Dp = H + W - 1 + 8; n.Hp = H + 4;
+    n.D = H + W - 1; n.HS = (H + 3) & ~3;
+    n.nsteps = nsteps; n.parts = (std::min(H, W) + 31) / 32; n.ndiag = std::min(G, n.D);
+    n.steps = steps_dev; n.ctr = ctr_dev; n.idx = idx_dev;
+    e.max_len = max_len;
+    e.C[0] = G;  // network input: one channel per group
+    for (int l = 0; l < WF_LAYERS; l++) e.C[l + 1] = G * (l == WF_LAYERS - 1 ? nlast : cpg);
+    size_t pb = 0;
+    for (int l = 0; l < WF_LAYERS; l++) {
+        WfLayerDev& L = n.L[l];
+        L.Cin = e.C[l]; L.Cout = e.C[l + 1];
+        L.cin_g = L.Cin / G; L.cout_g = L.Cout / G; L.cpg4 = (L.cout_g + 3) / 4; L.nchunk = G * L.cpg4;
+        L.nblk = (L.Cin + CB - 1) / CB; L.nqb = (L.cin_g + CB - 1) / CB; L.has_q = l != 0;
+        e.cpg4_max = std::max(e.cpg4_max, L.cpg4); e.nblk_max = std::max(e.nblk_max, L.nblk); e.nqb_max = std::max(e.nqb_max, L.nqb);
+        pb += 2 * (size_t)nsets * L.cpg4 * n.D * n.HS;
+    }
+    if (e.nblk_max > 32 || e.nqb_max > 32) { set_error("wavefront engine: too many channels"); return LIC360_ERR_ARG; }
+    for (int i = 0; i <= WF_LAYERS; i++) {
+        e.fc_floats[i] = (size_t)nsets * n.Dp * n.Hp * e.C[i];
+        LIC360_CUDA(cudaMalloc(&e.fc[i], e.fc_floats[i] * sizeof(float)));
+        if (i < WF_LAYERS) {
+            e.fp_floats[i] = (size_t)nsets * e.C[i] * n.D * n.HS;
+            LIC360_CUDA(cudaMalloc(&e.fp[i], e.fp_floats[i] * sizeof(float)));
+        }
+    }
+    e.pbuf_f4 = pb;
+    LIC360_CUDA(cudaMalloc(&e.pbuf, pb * sizeof(float4)));
+    LIC360_CUDA(cudaMemset(e.pbuf, 0, pb * sizeof(float4)));
+    float4* pp = e.pbuf;
+    for (int l = 0; l < WF_LAYERS; l++) {
+        WfLayerDev& L = n.L[l];
+        L.xp = e.fp[l]; L.xc = e.fc[l];
+        L.op = l + 1 < WF_LAYERS ? e.fp[l + 1] : nullptr;
+        L.oc = e.fc[l + 1];
+        L.rc = (l >= 2 && l <= 10 && (l % 2) == 0) ? e.fc[l - 1] : nullptr;  // conv2 of residual block b = layer 2b (y + x)
+        for (int par = 0; par < 2; par++) { L.pbuf[par] = pp; pp += (size_t)nsets * L.cpg4 * n.D * n.HS; }
+    }
+    // TMA descriptors: FP frame of layer l as a 3-D tensor {HS, D, nsets*Cin}, box {40, 9, 4}, zero fill outside
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("wavefront engine: cuTensorMapEncodeTiled is not available from this driver"); return LIC360_ERR_CUDA; }
+    for (int l = 0; l < WF_LAYERS; l++) {
+        const cuuint64_t dims[3] = {(cuuint64_t)n.HS, (cuuint64_t)n.D, (cuuint64_t)nsets * e.C[l]};
+        const cuuint64_t strides[2] = {(cuuint64_t)n.HS * 4, (cuuint64_t)n.D * n.HS * 4};
+        const cuuint32_t box[3] = {WF_BOX_W, 9, 4};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&e.maps.tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e.fp[l], dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
+    }
+    // launch shapes
+    e.old_smem = 128 + (size_t)e.nblk_max * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)e.nblk_max * 8;
+    e.prev_smem = (size_t)e.nqb_max * 32 * sizeof(float4);
+    // the attribute is per kernel, not per engine: only ever raise it (two engines with different channel counts share it)
+    static size_t old_attr = 48 * 1024, chain_attr = 48 * 1024;
+    if (e.old_smem > old_attr) {
+        LIC360_CUDA(cudaFuncSetAttribute(wf_old_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old_smem));
+        old_attr = e.old_smem;
+    }
+    e.cluster = 8;
+    if (const char* s = getenv("LIC360_WF_CLUSTER")) e.cluster = std::max(1, std::min(8, atoi(s)));
+    int items_max = 0, tasks_max = 0;
+    for (int l = 0; l < WF_LAYERS; l++) {
+        const int per = (max_len * n.L[l].cpg4 + e.cluster - 1) / e.cluster;
+        items_max = std::max(items_max, per);
+        tasks_max = std::max(tasks_max, per * (n.L[l].has_q ? n.L[l].nqb : 1));
+    }
+    // a kernel row of an item (5 activations + 20 weight vectors) is kept in registers: at most 384 threads per CTA
+    // (168 registers each); CTAs with more tasks loop
+    e.chain_threads = std::min(384, std::max(128, ((tasks_max + 31) / 32) * 32));
+    e.chain_smem = (size_t)tasks_max * sizeof(float4);
+    if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
+    if (e.chain_smem > chain_attr) {
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+        chain_attr = e.chain_smem;
+    }
+    return LIC360_OK;
+}
+
+void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope) {
+    WfLayerDev& L = e.dev.L[l];
+    L.wp = wp; L.wq = wq; L.bias = bias; L.slope = slope;
+}
+
+void wf_free(WfEngine& e) {
+    for (int i = 0; i <= WF_LAYERS; i++) { cudaFree(e.fp[i]); cudaFree(e.fc[i]); e.fp[i] = e.fc[i] = nullptr; }
+    cudaFree(e.pbuf);
+    e.pbuf = nullptr;
+}
+
+cudaError_t wf_clear(const WfEngine& e, cudaStream_t s) {
+    for (int i = 0; i <= WF_LAYERS; i++) {
+        cudaError_t r = cudaMemsetAsync(e.fc[i], 0, e.fc_floats[i] * sizeof(float), s);
+        if (r != cudaSuccess) return r;
+        if (i < WF_LAYERS && (r = cudaMemsetAsync(e.fp[i], 0, e.fp_floats[i] * sizeof(float), s)) != cudaSuccess) return r;
+    }
+    return cudaMemsetAsync(e.pbuf, 0, e.pbuf_f4 * sizeof(float4), s);
+}
+
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s) {
+    const WfNetDev& n = e.dev;
+    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, e.nblk_max);
+    const cudaError_t stale = cudaGetLastError();
+    wf_old_kernel<<<grid, block, e.old_smem, s>>>(n, e.maps, dp);
+    g_launches++;
+    const cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess || stale != cudaSuccess)
+        fprintf(stderr, "lic360: wf_old_kernel launch grid (%u,%u,%u) block (%u,%u) smem %zu -> %s (stale: %s)\n", grid.x, grid.y, grid.z,
+                block.x, block.y, e.old_smem, cudaGetErrorString(r), cudaGetErrorString(stale));
+    return r;
+}
+
+cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s) {
+    const WfNetDev& n = e.dev;
+    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, e.nqb_max);
+    if (e.nqb_max <= 10) wf_prev_kernel<320><<<grid, block, e.prev_smem, s>>>(n);
+    else wf_prev_kernel<1024><<<grid, block, e.prev_smem, s>>>(n);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s) {
+    const WfNetDev& n = e.dev;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n.nsets * e.cluster);
+    cfg.blockDim = dim3(e.chain_threads);
+    cfg.dynamicSmemBytes = e.chain_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = e.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = e.cluster > 1 ? 1 : 0;
+    g_launches++;
+    return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
+}
+
+}  // namespace lic360

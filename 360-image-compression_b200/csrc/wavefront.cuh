@@ -1,0 +1,75 @@
+// Wavefront engine of the fused decoder (wavefront.cu): data structures shared with codec.cu.
+//
+// One engine = the 12-layer context network of one bitstream (code stream: 48 groups x 3 nets, importance stream:
+// 1 group) in its decoder form.  Activations live in two persistent layouts per layer:
+//   FP  "planar skewed"   [set*C + c][D][HS]          d = h + w, HS = H rounded up to 4.  Source of the TMA box loads
+//                                                      of the old-term kernel (a 5x5 window of 32 diagonal neighbours
+//                                                      is the rectangle 36 x 9 in (h, d) coordinates).
+//   FC  "channel-last"    [set][D + 8][H + 4][C]      zero border of 4 diagonals / 2 rows: the previous- and
+//                                                      same-wavefront terms read one float4 (4 channels of a group)
+//                                                      per tap with no bounds checks.
+// Cells outside the image (w = d - h not in [0, W)) exist in both layouts, are never written and stay zero.
+#pragma once
+#include <cuda.h>
+#include "internal.cuh"
+
+namespace lic360 {
+
+constexpr int WF_LAYERS = 12;
+
+struct WfLayerDev {
+    const float* xp;     // FP input frame (nullptr never: every layer has one)
+    const float* xc;     // FC input frame
+    float* op;           // FP output frame (nullptr for the last layer: nobody convolves it)
+    float* oc;           // FC output frame
+    const float* rc;     // FC residual frame (same shape as oc) or nullptr
+    const float* wp;     // old-term weights      [set][chunk][ci][tap] float4
+    const float* wq;     // R / Q weights    [cls][set][chunk][tap][c]  float4
+    const float* bias;   // [set][Cout]
+    const float* slope;  // [set][Cout] or nullptr (no PReLU)
+    float4* pbuf[2];     // old-term sums P, then P + R, by step parity: [set][kc][D][HS]
+    int Cin, Cout, cin_g, cout_g, cpg4, nchunk, nblk, nqb, has_q, pad;
+};
+
+struct WfNetDev {
+    WfLayerDev L[WF_LAYERS];
+    const StepDesc* steps;  // [nsteps]
+    const int* ctr;         // current step (device counter, advanced at the end of every step graph)
+    const int32_t* idx;     // index plan (row plane, column plane), code_contex_cuda.cu:11-32
+    int nsets, G, H, W, D, HS, Dp, Hp, nsteps, parts, ndiag, pad;
+};
+
+struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer, box {40 h, 9 d, 4 c}
+
+struct WfEngine {
+    WfNetDev dev;
+    WfMaps maps;
+    float* fp[WF_LAYERS + 1] = {nullptr};
+    float* fc[WF_LAYERS + 1] = {nullptr};
+    size_t fp_floats[WF_LAYERS + 1] = {0}, fc_floats[WF_LAYERS + 1] = {0};
+    float4* pbuf = nullptr;
+    size_t pbuf_f4 = 0;
+    int C[WF_LAYERS + 1];
+    int max_len = 0, cpg4_max = 0, nblk_max = 0, nqb_max = 0;
+    int cluster = 1, chain_threads = 0;
+    size_t old_smem = 0, prev_smem = 0, chain_smem = 0;
+};
+
+// G groups, cpg hidden channels per group, nlast output channels per group of the last layer, latent H x W
+int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, const int32_t* idx_dev, const StepDesc* steps_dev,
+            const int* ctr_dev, int nsteps, int max_len);
+void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope);
+void wf_free(WfEngine& e);
+cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s);       // P of step *ctr + dp, all layers
+cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s);              // P + R of step *ctr, all layers
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s);             // the 12-layer chain of step *ctr
+
+__host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int C, int n, int d, int h) {
+    return (((size_t)n * Dp + d + 4) * Hp + h + 2) * C;
+}
+__host__ __device__ inline size_t wf_fp_index(int D, int HS, int C, int n, int c, int d, int h) {
+    return (((size_t)n * C + c) * D + d) * HS + h;
+}
+
+}  // namespace lic360

@@ -77,6 +77,8 @@ SIGNATURES = {
     "lic360_codec_stream_copy": (_L, [_P, _I, _P, _L]),
     "lic360_codec_decode": (_I, [_P, _P, _L, _P, _L, _P, _P]),
     "lic360_codec_last_timing": (_I, [_P, _P, _I]),
+    "lic360_codec_set_mode": (_I, [_P, _I]),
+    "lic360_codec_kernel_times": (_I, [_P, _I, _P, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

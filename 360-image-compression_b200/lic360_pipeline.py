@@ -114,6 +114,16 @@ class FusedCodec(object):
                                       mask.data_ptr()))
         return code, mask
 
+    def set_mode(self, mode):
+        """0: pipelined graph replay per step (default); 1: serialized launches with per-kernel CUDA-event timing."""
+        check(LIB.lic360_codec_set_mode(self._h, int(mode)))
+
+    def kernel_times(self, stream_id=0):
+        """After a mode-1 decode: ms spent per kernel class of one stream (0 = code, 1 = importance)."""
+        out = (ctypes.c_double * 5)()
+        check(LIB.lic360_codec_kernel_times(self._h, stream_id, out, 5))
+        return {'old_ms': out[0], 'prev_ms': out[1], 'chain_ms': out[2], 'scatter_rows_ms': out[3], 'steps': int(out[4])}
+
     def last_timing(self):
         out = (ctypes.c_double * 6)()
         LIB.lic360_codec_last_timing(self._h, out, 6)

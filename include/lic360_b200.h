@@ -203,6 +203,12 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
 /* milliseconds of the last encode/decode call: [0] total, [1] host arithmetic coder, [2] waiting for the GPU,
  * [3] importance stream part of a decode, [4] CUDA-event time of all decode graph replays, [5] of the importance stream ones */
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n);
+/* mode 0 (default): pipelined graph replay per wavefront step.  mode 1: the same kernels launched one by one on the codec
+ * stream with CUDA events between them (the decode is serialized and slower; used by bench.py for the roofline block). */
+int lic360_codec_set_mode(lic360_codec* c, int mode);
+/* after a mode-1 decode: total milliseconds of the last decode spent in [0] the old-term kernel, [1] the previous-wavefront
+ * kernel, [2] the 12-layer chain kernel, [3] scatter + CDF-row kernels, and [4] the number of steps, for one stream */
+int lic360_codec_kernel_times(lic360_codec* c, int stream_id, double* out, int n);
 
 #ifdef __cplusplus
 }
