@@ -185,7 +185,7 @@ __global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __res
         const float v = fmaf(scale, s, bias);
         for (int r = 0; r < rep; r++) {
             fp0[wf_fp_index(D, HS, G, r, tc, th + tw, th)] = v;
-            fc0[wf_fc_index(Dp, Hp, G, r, th + tw, th) + tc] = v;
+            fc0[wf_fc_index(Dp, Hp, G, 1, r, th + tw, tc, th)] = v;
         }
         if (keep) keep[th * W + tw] = s;  // importance stream: the decoded level itself
     }
@@ -199,7 +199,7 @@ __global__ void finish_code_kernel(const float* __restrict__ fc0, const float* _
     const int n = G * H * W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int w = i % W, h = (i / W) % H, g = i / (W * H);
-        out[i] = fc0[wf_fc_index(Dp, Hp, G, 0, h + w, h) + g] + bias * mask[i];
+        out[i] = fc0[wf_fc_index(Dp, Hp, G, 1, 0, h + w, g, h)] + bias * mask[i];
     }
 }
 
@@ -227,13 +227,12 @@ __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __r
         const int HW = H * W;
         const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
         const int tc = d.psum - th - tw;
-        const int C = G * 3;
         float wv[3], dv[3], mv[3], o[9];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            wv[i] = y[wf_fc_index(Dp, Hp, C, 0, th + tw, th) + tc * 3 + i];
-            dv[i] = y[wf_fc_index(Dp, Hp, C, 1, th + tw, th) + tc * 3 + i];
-            mv[i] = y[wf_fc_index(Dp, Hp, C, 2, th + tw, th) + tc * 3 + i];
+            wv[i] = y[wf_fc_index(Dp, Hp, G, 3, 0, th + tw, tc, th) + i];
+            dv[i] = y[wf_fc_index(Dp, Hp, G, 3, 1, th + tw, tc, th) + i];
+            mv[i] = y[wf_fc_index(Dp, Hp, G, 3, 2, th + tw, tc, th) + i];
         }
         gmm_row(wv, dv, mv, o, 3, 8, 3.5f, 65536.f, 1e-6f, s2);
         const size_t pos = ((size_t)tc * H + th) * W + tw;
@@ -262,7 +261,7 @@ __global__ void imp_rows_wf_kernel(const float* __restrict__ y, const int32_t* _
     if (l < d.len) {
         const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + H * W);
         float o[50];
-        const float* yp = y + wf_fc_index(Dp, Hp, 49, 0, th + tw, th);
+        const float* yp = y + wf_fc_index(Dp, Hp, 1, 49, 0, th + tw, 0, th);
         for (int i = 0; i < 49; i++) o[1 + i] = yp[i];
         entropy_row(o, 49, 65536.f);
         pack_imp_row(o, 0, rows + (size_t)l * 64);
@@ -354,9 +353,10 @@ static int check_params(const NetDesc& n) {
     return LIC360_OK;
 }
 
-// the kernels of one decode step, in stream order on `s` (critical branch); the old terms of the NEXT step go to `side`
-// when it is a different stream (graph capture: a parallel branch) -- they only read wavefronts <= p-1, complete once
-// the scatter of step p-1's symbols has run.
+// the kernels of one decode step in stream order.  The old terms of the NEXT step come last: the host is released by
+// the flag that the rows kernel raises, so this launch (the bulk of the arithmetic) overlaps the host arithmetic decoder.
+// (A parallel graph branch does not help: the chain kernel's clusters need whole SMs and would wait for this kernel's
+// CTAs to drain anyway.)
 // ev != nullptr: profile mode, events bracket the kernel classes (everything on `s`).
 #define WF_DEBUG_SYNC(what)                                                                               \
     do {                                                                                                \
@@ -379,13 +379,6 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
         scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
-    if (side != s) {
-        // fork AFTER the scatter: the old terms of step p+1 read the symbols of wavefront p-1 that it just wrote
-        LIC360_CUDA(cudaEventRecord(c->ev_fork, s));
-        LIC360_CUDA(cudaStreamWaitEvent(side, c->ev_fork, 0));
-        LIC360_CUDA(wf_launch_old(n.wf, 1, side));
-        LIC360_CUDA(cudaEventRecord(c->ev_join, side));
-    }
     WF_DEBUG_SYNC("scatter kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
     LIC360_CUDA(wf_launch_prev(n.wf, s));
@@ -404,8 +397,8 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
-    if (side != s) LIC360_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
-    else LIC360_CUDA(wf_launch_old(n.wf, 1, s));
+    (void)side;
+    LIC360_CUDA(wf_launch_old(n.wf, 1, s));
     WF_DEBUG_SYNC("old-term kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
     advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);

@@ -86,21 +86,22 @@ __device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp) {
 }
 
 // ------------------------------------------------------------------------------------------------ old terms (P)
-// CTA = 32 consecutive positions of one anti-diagonal x one 4-channel output chunk x (layer, net); warp j = canonical
-// 16-channel input block j.  Per stage of 4 input channels ONE 3-D TMA box {36 h, 9 d, 4 c} of the planar skewed frame
+// CTA = 32 consecutive positions of one anti-diagonal x one 4-channel output chunk x (layer, net); its 4 warps share
+// out the canonical 16-channel input blocks that have old terms for this output group.  Per stage of 4 input channels ONE 3-D TMA box {36 h, 9 d, 4 c} of the planar skewed frame
 // (out-of-image cells zero-filled by the TMA unit: no index math, no bounds checks) plus one bulk copy of the stage's
 // 100 float4 weights land in the warp's private shared-memory slice and complete on the warp's own mbarrier.
-__global__ void __launch_bounds__(1024) wf_old_kernel(const __grid_constant__ WfNetDev net, const __grid_constant__ WfMaps maps,
-                                                    int dp) {
+constexpr int WF_OLD_WARPS = 4;  // warps per CTA; warp w walks the canonical blocks w, w+4, ... that have old terms
+
+__global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_constant__ WfNetDev net,
+                                                                  const __grid_constant__ WfMaps maps, int dp) {
     extern __shared__ unsigned char wf_raw[];
     const WfTile t = wf_tile(net, dp);
     if (!t.ok) return;  // CTA-uniform
     const WfLayerDev& L = net.L[t.l];
-    const int nseg = blockDim.y;
     const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
-    unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                     // 128-B aligned
-    float4* part = reinterpret_cast<float4*>(base + (size_t)nseg * WF_STAGE_BYTES);      // [nseg][32]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + nseg * 32);  // [nseg]
+    unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
+    float4* part = reinterpret_cast<float4*>(base + (size_t)WF_OLD_WARPS * WF_STAGE_BYTES);    // [nblk][32]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + L.nblk * 32);      // [WF_OLD_WARPS]
     const int lane = threadIdx.x, seg = threadIdx.y;
     float* band = reinterpret_cast<float*>(base + (size_t)seg * WF_STAGE_BYTES);
     float4* wsm = reinterpret_cast<float4*>(band + DC_STAGE * WF_BAND);
@@ -114,33 +115,34 @@ __global__ void __launch_bounds__(1024) wf_old_kernel(const __grid_constant__ Wf
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (seg < L.nblk) {
-        const int Cin = L.Cin;
-        const int lim = min(Cin, (t.tc + 3) * L.cin_g);  // old terms: g_in <= tc + 2
-        const int cb = min(CB, Cin - seg * CB);
-        const int chunk = t.tc * L.cpg4 + t.kc;
-        const float4* wp4 = reinterpret_cast<const float4*>(L.wp) + (((size_t)t.n * L.nchunk + chunk) * Cin + seg * CB) * TAPS;
-        unsigned phase = 0;
-        for (int c0 = 0; c0 < cb && seg * CB + c0 < lim; c0 += DC_STAGE) {
+    const int Cin = L.Cin;
+    const int lim = min(Cin, (t.tc + 3) * L.cin_g);  // old terms: g_in <= tc + 2
+    const int nact = (lim + CB - 1) / CB;            // canonical blocks that have old terms
+    const int chunk = t.tc * L.cpg4 + t.kc;
+    unsigned phase = 0;
+    for (int j = seg; j < nact; j += WF_OLD_WARPS) {
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int cb = min(CB, Cin - j * CB);
+        const float4* wp4 = reinterpret_cast<const float4*>(L.wp) + (((size_t)t.n * L.nchunk + chunk) * Cin + j * CB) * TAPS;
+        for (int c0 = 0; c0 < cb && j * CB + c0 < lim; c0 += DC_STAGE) {
             const int nc = min(DC_STAGE, cb - c0);
             __syncwarp();  // every lane is done with the previous stage
             if (lane == 0) {
                 mbar_expect_tx(bar, WF_BAND_BYTES + nc * TAPS * 16);
-                tma_load_3d(band_s, &maps.tm[t.l], h0, t.d - 4, t.n * Cin + seg * CB + c0, bar);
+                tma_load_3d(band_s, &maps.tm[t.l], h0, t.d - 4, t.n * Cin + j * CB + c0, bar);
                 bulk_load(wsm_s, wp4 + c0 * TAPS, nc * TAPS * 16, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
-            dc_stage_fma<1, WF_BOX_W, WF_BAND>(bandl, wsm, nc, lane, seg * CB + c0, L.cin_g, t.tc, u);
+            dc_stage_fma<1, WF_BOX_W, WF_BAND>(bandl, wsm, nc, lane, j * CB + c0, L.cin_g, t.tc, u);
         }
+        part[j * 32 + lane] = u;
     }
-    part[seg * 32 + lane] = u;
     __syncthreads();
     const int h = t.hbase + lane;
     if (seg == 0 && h <= t.hmax) {
         float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < L.nblk; j++) {
+        for (int j = 0; j < nact; j++) {  // blocks without old terms add nothing (the encoder skips them too)
             const float4 v = part[j * 32 + lane];
             P.x = P.x + v.x; P.y = P.y + v.y; P.z = P.z + v.z; P.w = P.w + v.w;
         }
@@ -169,9 +171,10 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
     const int cend = min((jq + 1) * CB, cin_g);
     const float4* w = reinterpret_cast<const float4*>(L.wq) +
                       ((size_t)(cls * net.nsets + n) * L.nchunk + tc * L.cpg4 + kc) * TAPS * cin_g;
-    // cell (d-4+kh+kw, h-2+kh) of the padded channel-last frame = xb + ((kh+kw) * Hp + kh) * C
-    const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.Hp + h) * C;
-    const int Hp = net.Hp;
+    // cell (d-4+kh+kw, group gq, h-2+kh) of the padded frame = xb + (((kh+kw) * G + gq) * Hp + kh) * cin_g
+    const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.G * net.Hp + h) * cin_g;
+    const int Hp = net.Hp, G = net.G;
+    (void)C;
     if ((cin_g & 3) == 0 && net.G == 1) {
         // one group: input group 0 is selected by exactly the taps with kh + kw == gsel0 (3 or 4)
         for (int c0 = jq * CB; c0 < cend; c0 += 4) {
@@ -181,7 +184,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                 const int kw = gsel0 - kh;
                 const bool ok = kw >= 0 && kw < 5;
                 xv[kh] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) xv[kh] = wf_ldx4<CG>(xb + ((size_t)gsel0 * Hp + kh) * C + c0);
+                if (ok) xv[kh] = wf_ldx4<CG>(xb + ((size_t)gsel0 * Hp + kh) * cin_g + c0);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     wv[kh][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -213,7 +216,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                     const int gq = gsel0 - kh - kw;
                     const bool ok = gq >= 0 && gq < net.G;
                     xv[kw] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) xv[kw] = wf_ldx4<CG>(xb + ((size_t)(kh + kw) * Hp + kh) * C + gq * cin_g + c0);
+                    if (ok) xv[kw] = wf_ldx4<CG>(xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         wv[kw][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,7 +247,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                 for (int kw = 0; kw < 5; kw++) {
                     const int gq = gsel0 - kh - kw;
                     if (gq < 0 || gq >= net.G) continue;
-                    const float* xp = xb + ((size_t)(kh + kw) * Hp + kh) * C + gq * cin_g + c0;
+                    const float* xp = xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0;
                     const float4* wt = w + (kh * 5 + kw) * cin_g + c0;
                     for (int c = 0; c < nc; c++) {
                         const float xx = CG ? __ldcg(xp + c) : __ldg(xp + c);
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
             const int d = h + w, tc = sd.psum - d;
             // independent loads first: P + R, bias, slope, residual
             const float4 pr = __ldg(L.pbuf[sd.psum & 1] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
-            const size_t fc = wf_fc_index(net.Dp, net.Hp, L.Cout, n, d, h) + tc * L.cout_g + kc * 4;
+            const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h) + kc * 4;
             const int o0 = tc * L.cout_g + kc * 4;
             float bs[4], sl[4], rs[4];
 #pragma unroll
@@ -369,6 +372,143 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
             }
         }
         if (l + 1 < WF_LAYERS) {
+            if (nc > 1) cg::this_cluster().sync();
+            else __syncthreads();
+        }
+    }
+}
+
+// Fast chain for nets whose chained layers have 4 channels per input group and at most 4 per output group (the code
+// stream: 48 groups x 4): one item = one slab position.  Everything that does not depend on the layer below is taken
+// off the per-layer critical path:
+//   - the same-wavefront weights of layer l+1 (one 100-float4 row per output group present in this CTA's item range)
+//     are copied to shared memory with cp.async while layer l is being computed,
+//   - P + R, bias, slope and the residual of layer l+1 are loaded into registers before the barrier that ends layer l,
+//   - the 25 activation loads of an item (one float4 per tap) are all in flight before the first FMA.
+// Per layer that leaves: cluster barrier -> one L2 round trip -> 400 FMAs against shared-memory weights -> stores.
+constexpr int WF_ROW_F4 = TAPS * 4;  // float4 per (output group) row of same-wavefront weights when cin_g == 4
+
+struct WfPre { float4 pr; float bs[4], sl[4], rs[4]; };
+
+__device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const WfLayerDev& L, int n, int par, int d, int h, int tc,
+                                                   WfPre& p) {
+    p.pr = __ldg(L.pbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
+    const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h);
+    const int o0 = tc * L.cout_g;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const bool live = q < L.cout_g;
+        p.bs[q] = live ? __ldg(L.bias + n * L.Cout + o0 + q) : 0.f;
+        p.sl[q] = live && L.slope ? __ldg(L.slope + n * L.Cout + o0 + q) : 0.f;
+        p.rs[q] = live && L.rc ? __ldcg(L.rc + fc + q) : 0.f;  // written by this very thread two layers ago
+    }
+}
+
+__global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant__ WfNetDev net, int nc, int rows_cap) {
+    extern __shared__ float4 wf_wsm[];  // [2][rows_cap][WF_ROW_F4]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    const StepDesc sd = net.steps[*net.ctr];
+    const int HW = net.H * net.W, par = sd.psum & 1;
+    const int per = (sd.len + nc - 1) / nc;
+    const int i0 = min(sd.len, rank * per), i1 = min(sd.len, i0 + per), nloc = i1 - i0;
+    // plan order is diagonal-major, so the output groups of this CTA's items are the contiguous range [tc_lo, tc_hi]
+    int tc_lo = 0, nrows = 0;
+    if (nloc > 0) {
+        const int ka = sd.start + i0, kb = sd.start + i1 - 1;
+        const int tc_hi = sd.psum - __ldg(net.idx + ka) - __ldg(net.idx + ka + HW);
+        tc_lo = sd.psum - __ldg(net.idx + kb) - __ldg(net.idx + kb + HW);
+        nrows = tc_hi - tc_lo + 1;
+    }
+    // slot 0 item of this thread (the only one unless the slab is larger than the cluster's thread count)
+    const bool has0 = tid < nloc;
+    int h0 = 0, d0 = 0, tc0 = 0;
+    if (has0) {
+        const int k = sd.start + i0 + tid;
+        h0 = __ldg(net.idx + k);
+        d0 = h0 + __ldg(net.idx + k + HW);
+        tc0 = sd.psum - d0;
+    }
+    WfPre pre;
+    if (has0) wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
+    for (int l = 0; l < WF_LAYERS; l++) {
+        const WfLayerDev& L = net.L[l];
+        // stage the same-wavefront weights of the next layer: rows tc_lo .. tc_lo + nrows - 1 are contiguous in wq
+        if (l + 1 < WF_LAYERS && nrows > 0) {
+            const WfLayerDev& Ln = net.L[l + 1];
+            const float4* src = reinterpret_cast<const float4*>(Ln.wq) + ((size_t)(net.nsets + n) * Ln.nchunk + tc_lo) * WF_ROW_F4;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(wf_wsm + (size_t)((l + 1) & 1) * rows_cap * WF_ROW_F4);
+            for (int e = tid; e < nrows * WF_ROW_F4; e += nt) cp_async16(dst + 16u * e, src + e);
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        const float4* wl = wf_wsm + (size_t)(l & 1) * rows_cap * WF_ROW_F4;
+        for (int il = tid; il < nloc; il += nt) {
+            int h = h0, d = d0, tc = tc0;
+            WfPre p = pre;
+            if (il != tid) {  // further slots: nothing was prefetched
+                const int k = sd.start + i0 + il;
+                h = __ldg(net.idx + k);
+                d = h + __ldg(net.idx + k + HW);
+                tc = sd.psum - d;
+                wf_chain4_prefetch(net, L, n, par, d, h, tc, p);
+            }
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (L.has_q) {
+                const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.G * net.Hp + h) * 4;
+                const float4* wr = wl + (size_t)(tc - tc_lo) * WF_ROW_F4;
+                float4 xv[TAPS];
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = tc + 4 - kh - kw;
+                        xv[kh * 5 + kw] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (gq >= 0 && gq < net.G)
+                            xv[kh * 5 + kw] = __ldcg(reinterpret_cast<const float4*>(xb + (((size_t)(kh + kw) * net.G + gq) * net.Hp + kh) * 4));
+                    }
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = tc + 4 - kh - kw;
+                        if (gq < 0 || gq >= net.G) continue;
+                        const float4 x4 = xv[kh * 5 + kw];
+                        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const float4 w4 = wr[(kh * 5 + kw) * 4 + c];
+                            u.x = fmaf(xs[c], w4.x, u.x);
+                            u.y = fmaf(xs[c], w4.y, u.y);
+                            u.z = fmaf(xs[c], w4.z, u.z);
+                            u.w = fmaf(xs[c], w4.w, u.w);
+                        }
+                    }
+            }
+            const float Q[4] = {0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w};  // Q = 0 + q_0 (one canonical block)
+            const float PR[4] = {p.pr.x, p.pr.y, p.pr.z, p.pr.w};
+            const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h);
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q] = 0.f;
+                if (q >= L.cout_g) continue;
+                float y = (PR[q] + Q[q]) + p.bs[q];
+                if (L.slope) y = y > 0.f ? y : y * p.sl[q];
+                if (L.rc) y = y + p.rs[q];
+                v[q] = y;
+                if (L.op) L.op[wf_fp_index(net.D, net.HS, L.Cout, n, tc * L.cout_g + q, d, h)] = y;
+            }
+            if (L.cout_g == 4) {
+                *reinterpret_cast<float4*>(L.oc + fc) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < L.cout_g) L.oc[fc + q] = v[q];
+            }
+        }
+        if (l + 1 < WF_LAYERS) {
+            if (has0) wf_chain4_prefetch(net, net.L[l + 1], n, par, d0, h0, tc0, pre);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             if (nc > 1) cg::this_cluster().sync();
             else __syncthreads();
         }
@@ -446,7 +586,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
     }
     // launch shapes
-    e.old_smem = 128 + (size_t)e.nblk_max * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)e.nblk_max * 8;
+    e.old_smem = 128 + (size_t)WF_OLD_WARPS * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
     e.prev_smem = (size_t)e.nqb_max * 32 * sizeof(float4);
     // the attribute is per kernel, not per engine: only ever raise it (two engines with different channel counts share it)
     static size_t old_attr = 48 * 1024, chain_attr = 48 * 1024;
@@ -466,9 +606,14 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     // (168 registers each); CTAs with more tasks loop
     e.chain_threads = std::min(384, std::max(128, ((tasks_max + 31) / 32) * 32));
     e.chain_smem = (size_t)tasks_max * sizeof(float4);
+    e.chain4 = G > 1 && G <= 64;
+    for (int l = 0; l < WF_LAYERS; l++) e.chain4 = e.chain4 && n.L[l].cpg4 == 1 && (l == 0 || n.L[l].cin_g == 4);
+    if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = false;
+    if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
     if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
     if (e.chain_smem > chain_attr) {
         LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
         chain_attr = e.chain_smem;
     }
     return LIC360_OK;
@@ -496,7 +641,7 @@ cudaError_t wf_clear(const WfEngine& e, cudaStream_t s) {
 
 cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s) {
     const WfNetDev& n = e.dev;
-    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, e.nblk_max);
+    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, WF_OLD_WARPS);
     const cudaError_t stale = cudaGetLastError();
     wf_old_kernel<<<grid, block, e.old_smem, s>>>(n, e.maps, dp);
     g_launches++;
@@ -530,6 +675,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
+    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }
 

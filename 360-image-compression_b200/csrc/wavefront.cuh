@@ -5,9 +5,10 @@
 //   FP  "planar skewed"   [set*C + c][D][HS]          d = h + w, HS = H rounded up to 4.  Source of the TMA box loads
 //                                                      of the old-term kernel (a 5x5 window of 32 diagonal neighbours
 //                                                      is the rectangle 36 x 9 in (h, d) coordinates).
-//   FC  "channel-last"    [set][D + 8][H + 4][C]      zero border of 4 diagonals / 2 rows: the previous- and
+//   FC  "group-major channel-last"  [set][D + 8][G][H + 4][C/G]   zero border of 4 diagonals / 2 rows: the previous- and
 //                                                      same-wavefront terms read one float4 (4 channels of a group)
-//                                                      per tap with no bounds checks.
+//                                                      per tap with no bounds checks, and the 32 lanes of a warp
+//                                                      (consecutive h on one diagonal, one group) read 512 contiguous bytes.
 // Cells outside the image (w = d - h not in [0, W)) exist in both layouts, are never written and stay zero.
 #pragma once
 #include <cuda.h>
@@ -52,6 +53,7 @@ struct WfEngine {
     int C[WF_LAYERS + 1];
     int max_len = 0, cpg4_max = 0, nblk_max = 0, nqb_max = 0;
     int cluster = 1, chain_threads = 0;
+    bool chain4 = false;  // every chained layer has 4 channels per group: the staged-weight chain kernel applies
     size_t old_smem = 0, prev_smem = 0, chain_smem = 0;
 };
 
@@ -65,8 +67,9 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s);       // P
 cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s);              // P + R of step *ctr, all layers
 cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s);             // the 12-layer chain of step *ctr
 
-__host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int C, int n, int d, int h) {
-    return (((size_t)n * Dp + d + 4) * Hp + h + 2) * C;
+// first channel of group g at (d, h); cpg = channels per group of that frame
+__host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int G, int cpg, int n, int d, int g, int h) {
+    return ((((size_t)n * Dp + d + 4) * G + g) * Hp + h + 2) * cpg;
 }
 __host__ __device__ inline size_t wf_fp_index(int D, int HS, int C, int n, int c, int d, int h) {
     return (((size_t)n * C + c) * D + d) * HS + h;
