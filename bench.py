@@ -12,7 +12,8 @@ collective on the codec path), so scaling is weak: value = N * 0.
 `value`  : inputs resident in HBM, outputs left in HBM.
 `e2e`    : the same call with the latent in pinned HOST memory: H2D of (code, mask, importance levels) and D2H of the
            decoded (code, mask) inside the timed region.
-`roofline`: dominant kernel = the wavefront context conv (cconv_dc_kernel, 12 launches per decode step).
+`roofline`: dominant kernel = wf_old_kernel (old terms of all 12 context-conv layers of a wavefront step, TMA-fed),
+           timed with CUDA events on the codec stream in one extra serialized decode.
 `cpu_baseline` / `--impl reference`: the CPU rendition (oracle/: OpenMP restatement of the conv/table ops + the
            reference's own host arithmetic coder when oracle/_ref is built) on a bounded sample, all host threads.
 """
@@ -67,36 +68,33 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ algorithmic work
-def dc_algorithmic_bytes():
-    """Algorithmic bytes of one wavefront-conv launch, averaged over the 12 layers x 238 steps of one code-stream
-    decode: non-zero weights of the output groups present in the slab (read once), the inputs that carry
-    a non-zero weight for at least one slab output (read once), the slab outputs (written once); fp32, 3 nets."""
+def old_kernel_algorithmic_bytes():
+    """Algorithmic bytes of one launch of the dominant kernel, wf_old_kernel (old terms of all 12 layers x 3 nets of one
+    code-stream wavefront step), averaged over the 238 steps of a decode: the non-zero old-term weights
+    of the output groups present in the slab (read once), the activations of wavefronts <= p-2 that carry a non-zero
+    weight for at least one slab output (read once), and the P sums (16 B per slab position, layer and net, written once)."""
     import numpy as np
     npos = np.zeros(H + W - 1, np.int64)
     for d in range(H + W - 1):
         npos[d] = min(d, H - 1) - max(0, d - W + 1) + 1
-    layers = [(1, 4, 5)] + [(4, 4, 6)] * 10 + [(4, 3, 6)]
-    total, launches = 0, 0
-    for cin, cout, con in layers:
-        # non-zero weights per output group g: taps (kh,kw) x allowed input groups
-        nnz_g = np.zeros(G, np.int64)
+    layers = [(1, 4)] + [(4, 4)] * 10 + [(4, 3)]
+    nsteps = H + W + G - 2
+    total = 0
+    for cin, cout in layers:
+        nnz_g = np.zeros(G, np.int64)  # old-term weights of output group g: taps (kh,kw) x input groups <= g + 2 - s
         for g in range(G):
-            for s in range(9):  # s = kh + kw, number of taps with that sum
+            for s in range(9):
                 ntap = min(s, 8 - s) + 1
-                allowed = g + 4 - s + (1 if con == 6 else 0)
-                nnz_g[g] += ntap * max(0, min(G, allowed)) * cin * cout
-        for psum in range(H + W + G - 2):
+                nnz_g[g] += ntap * max(0, min(G, g + 3 - s)) * cin * cout
+        for psum in range(nsteps):
             la, lb = max(0, psum - G + 1), min(psum, H + W - 2)
-            groups = [psum - d for d in range(la, lb + 1)]
-            wbytes = 4 * 3 * sum(int(nnz_g[g]) for g in groups)
-            obytes = 4 * 3 * cout * int(npos[la:lb + 1].sum())
+            wbytes = 4 * 3 * sum(int(nnz_g[psum - d]) for d in range(la, lb + 1))
+            obytes = 16 * 3 * int(npos[la:lb + 1].sum())
             ibytes = 0
             for e in range(max(0, la - 4), min(H + W - 2, lb + 4) + 1):
-                ng = psum - e + (1 if con == 6 else 0)
-                ibytes += 4 * 3 * cin * int(npos[e]) * max(0, min(G, ng))
+                ibytes += 4 * 3 * cin * int(npos[e]) * max(0, min(G, psum - 1 - e))
             total += wbytes + obytes + ibytes
-            launches += 1
-    return total / launches, launches
+    return total / nsteps, nsteps
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -229,8 +227,13 @@ def main():
     value = world * MPX * args.steps / (ms / 1e3)
     e2e_value = world * MPX * args.steps / (ms_e2e / 1e3)
     mean = lambda k, xs: sum(x[k] for x in xs) / len(xs)
-    # ---- roofline of the dominant kernel
-    alg_bytes, n_dc_code = dc_algorithmic_bytes()
+    # ---- roofline of the dominant kernel: one more decode with the same kernels launched one by one on the codec stream
+    # and CUDA events between them (lic360_codec_set_mode(1)); wf_old_kernel launches once per wavefront step
+    codec.set_mode(1)
+    codec.decode(*codec.encode(tq, tm, tl))
+    kt, kt_imp = codec.kernel_times(0), codec.kernel_times(1)
+    codec.set_mode(0)
+    alg_bytes, n_old = old_kernel_algorithmic_bytes()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -239,19 +242,17 @@ def main():
     peak = peaks.get("hbm_gbs", 6650.0)
     prof = {}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "dc_kernel_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "old_kernel_summary.json")))
     except Exception:
         pass
-    gpu_steps_ms = mean("gpu_steps_ms", timing["dec"])
-    code_share = 1.0 - mean("imp_gpu_steps_ms", timing["dec"]) / max(gpu_steps_ms, 1e-9)
-    dc_share = prof.get("dc_share_of_step", 0.95)
-    dc_launch_us = gpu_steps_ms * code_share * dc_share / n_dc_code * 1e3
-    achieved = alg_bytes / (dc_launch_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "cconv_dc_kernel (wavefront context conv, code stream)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_us": dc_launch_us, "launches_per_decode": n_dc_code,
+    old_launch_us = kt["old_ms"] / max(kt["steps"], 1) * 1e3
+    achieved = alg_bytes / (old_launch_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "wf_old_kernel (TMA-fed old-term context conv of all 12 layers x 3 nets of a wavefront step, code stream)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": old_launch_us, "launches_per_decode": n_old,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "note": "launch time = CUDA-event time of the decode graph replays on the codec stream x kernel share from profiles/ (see DESIGN.md s5)"}
+                "kernel_ms_per_decode": {"code": kt, "importance": kt_imp},
+                "note": "avg launch = CUDA-event time around every wf_old_kernel launch of one serialized decode on the codec stream (DESIGN.md s5)"}
     line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
@@ -263,7 +264,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline,
             "breakdown_ms": {"encode": mean("total_ms", timing["enc"]), "encode_host_coder": mean("host_coder_ms", timing["enc"]),
                              "decode": mean("total_ms", timing["dec"]), "decode_host_coder": mean("host_coder_ms", timing["dec"]),
-                             "decode_importance_stream": mean("imp_stream_ms", timing["dec"]), "decode_gpu_graph_replays": gpu_steps_ms},
+                             "decode_importance_stream": mean("imp_stream_ms", timing["dec"]), "decode_waiting_for_gpu": mean("gpu_wait_ms", timing["dec"])},
             "bitstream": {"imp_bytes": nbytes[0], "code_bytes": nbytes[1], "bpp": (nbytes[0] + nbytes[1]) * 8 / (512 * 1024), "round_trip_exact": ok}}
     if sampler:
         line["clocks"] = sampler.summary()
