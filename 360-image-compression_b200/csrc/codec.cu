@@ -524,7 +524,7 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
     if (rc == LIC360_OK) rc = check_params(c->imp);
     if (rc) return rc;
     const auto t0 = clk::now();
-    c->t_host_coder = 0; c->t_gpu_wait = 0;
+    c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_imp = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0;
     cudaStream_t s = c->stream;
     // ---- importance stream (lic360_demo.py:173-189): Scale(-1, 2/47) -> net -> rows of all 2048 symbols
     {
@@ -538,8 +538,10 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
         LAUNCH_CHECK();
         LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 128, cudaMemcpyDeviceToHost, s));
         auto tw = clk::now();
+        c->t_gpu_steps_imp = ms_since(t0);  // host time spent enqueueing the importance-stream work
         LIC360_CUDA(cudaStreamSynchronize(s));
         c->t_gpu_wait += ms_since(tw);
+        c->t_imp = ms_since(t0);
         auto th = clk::now();
         lic360_coder_start_encoder_mem(c->coder[1]);
         rc = coder_encode_packed_imp(c->coder[1], c->rows_host, n.total_rows);
@@ -550,6 +552,7 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
     // ---- code stream (lic360_demo.py:124-141)
     {
         NetDesc& n = c->code;
+        const auto tq0 = clk::now();
         const int nel = n.G * n.H * n.W;
         prep_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(code_dev, mask_dev, n.frame[0], nel, 3.5f);
         LAUNCH_CHECK();
@@ -559,6 +562,7 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
                                                           c->ctr_dev, c->rows_dev, n.G, n.H, n.W, 1, (float)(1. / sqrt(2.0)));
         LAUNCH_CHECK();
         LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 16, cudaMemcpyDeviceToHost, s));
+        c->t_gpu_steps = ms_since(tq0);  // host time spent enqueueing the code-stream work
         auto tw = clk::now();
         LIC360_CUDA(cudaStreamSynchronize(s));
         c->t_gpu_wait += ms_since(tw);

@@ -81,7 +81,7 @@ __global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// EC: implicit-GEMM style SIMT kernel. One CTA = 8x32 positions x 32 output channels (8 chunks) of one image.
+// EC, first pass (old terms P): implicit-GEMM style SIMT kernel. One CTA = 8x32 positions x 32 output channels (8 chunks) of one image.
 // Thread tile = 4 positions (along w) x 2 chunks x 4 channels = 32 accumulators; K loop over 16-channel
 // blocks staged in shared memory (x tile with halo + masked weight tile), 25 taps unrolled.
 // ---------------------------------------------------------------------------------------------------------
@@ -140,18 +140,24 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
                 for (int p = 0; p < 4; p++)
 #pragma unroll
                     for (int q = 0; q < 4; q++) u[c][p][q] = 0.f;
+            // old taps of input group g for output group g_out: kh + kw <= g_out + 2 - g; beyond smax both chunks of
+            // this thread carry zero weights (warp-uniform skip; a single-group net keeps 6 of its 25 taps)
+            const int gmax_out = min(cA + 1, a.nchunk - 1) / a.cpg4;
 #pragma unroll 1
             for (int ci = 0; ci < cb; ci++) {
                 const float4* wA = ws4 + ((2 * tz) * CB + ci) * TAPS;
                 const float4* wB = ws4 + ((2 * tz + 1) * CB + ci) * TAPS;
+                const int smax = gmax_out + 2 - (j * CB + ci) / a.cin_g;
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++) {
+                    if (kh > smax) break;
                     const float* xr = xs + (ci * XH + ty + kh) * XW + 4 * tx;
                     float4 x0 = *reinterpret_cast<const float4*>(xr);
                     float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
                     float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                     for (int kw = 0; kw < 5; kw++) {
+                        if (kh + kw > smax) break;
                         float4 a4 = wA[kh * 5 + kw], b4 = wB[kh * 5 + kw];
 #pragma unroll
                         for (int p = 0; p < 4; p++) {
@@ -178,80 +184,96 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
         __syncthreads();
     }
 
-    // previous-wavefront (R) and same-wavefront (Q) terms + epilogue
+    // P of every output goes to `out`; cconv_ec_rq_kernel adds the R / Q terms and the epilogue in place
     const int h = h0 + ty;
-    const float4* wq4 = reinterpret_cast<const float4*>(a.wq);
-    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * TAPS * a.cin_g;  // float4 per class
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
         const int chunk = cA + cc;
         if (chunk >= a.nchunk || h >= H) continue;
         const int g_out = chunk / a.cpg4;
-        float RQ[2][4][4];
-#pragma unroll
-        for (int cls = 0; cls < 2; cls++) {
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) RQ[cls][p][q] = 0.f;
-            if (cls == 1 && !a.has_q) continue;
-            for (int jq = 0; jq * CB < a.cin_g; jq++) {
-                float qq[4][4];
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) qq[p][q] = 0.f;
-                const int cend = min((jq + 1) * CB, a.cin_g);
-                for (int c0 = jq * CB; c0 < cend; c0 += 4) {
-                    const int c1 = min(c0 + 4, cend);
-                    for (int kh = 0; kh < 5; kh++) {
-                        const int ph = h + kh - 2;
-                        if (ph < 0 || ph >= H) continue;
-                        for (int kw = 0; kw < 5; kw++) {
-                            const int gq = g_out + 3 + cls - kh - kw;
-                            if (gq < 0 || gq >= a.G) continue;
-                            const float4* wrow = wq4 + cls * wq_cls + (((size_t)set * a.nchunk + chunk) * TAPS + kh * 5 + kw) * a.cin_g;
-                            const float* xrow = a.x + (((size_t)n * Cin + gq * a.cin_g) * H + ph) * W;
-                            for (int c = c0; c < c1; c++) {
-                                const float4 w4 = __ldg(wrow + c);
-#pragma unroll
-                                for (int p = 0; p < 4; p++) {
-                                    const int pw = w0 + 4 * tx + p + kw - 2;
-                                    if (pw < 0 || pw >= W) continue;
-                                    const float xx = __ldg(xrow + (size_t)c * H * W + pw);
-                                    qq[p][0] = fmaf(xx, w4.x, qq[p][0]);
-                                    qq[p][1] = fmaf(xx, w4.y, qq[p][1]);
-                                    qq[p][2] = fmaf(xx, w4.z, qq[p][2]);
-                                    qq[p][3] = fmaf(xx, w4.w, qq[p][3]);
-                                }
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) RQ[cls][p][q] = RQ[cls][p][q] + qq[p][q];
-            }
-        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int oc = (chunk % a.cpg4) * 4 + q;
             if (oc >= a.cout_g) continue;
-            const int o = g_out * a.cout_g + oc;
-            const float b = __ldg(a.bias + set * a.Cout + o);
-            const float sl = a.slope ? __ldg(a.slope + set * a.Cout + o) : 0.f;
-            const size_t row = (((size_t)n * a.Cout + o) * H + h) * W;
+            const size_t row = (((size_t)n * a.Cout + g_out * a.cout_g + oc) * H + h) * W;
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 const int w = w0 + 4 * tx + p;
-                if (w >= W) continue;
-                float v = ((P[cc][p][q] + RQ[0][p][q]) + RQ[1][p][q]) + b;
-                if (a.slope) v = v > 0.f ? v : v * sl;
-                if (a.resid) v = v + a.resid[row + w];
-                a.out[row + w] = v;
+                if (w < W) a.out[row + w] = P[cc][p][q];
             }
         }
+    }
+}
+
+// EC, second pass: one thread = one position x one 4-channel output chunk.  Adds the previous-wavefront (R) and
+// same-wavefront (Q) terms -- every tap reads the cin_g channels of ONE input group -- to the P sums that
+// cconv_ec_kernel left in `out`, then bias / PReLU / residual, in place.  CTA = 256 consecutive positions of one
+// (image, chunk): the chunk's R and Q weights are staged once in shared memory and read as broadcasts; the activation
+// loads are coalesced along w.
+constexpr int RQ_THREADS = 256;
+
+__global__ void __launch_bounds__(RQ_THREADS, 3) cconv_ec_rq_kernel(const ConvArgs a) {
+    extern __shared__ float4 rq_wsm[];  // [2 classes][TAPS][cin_g]
+    const int chunk = blockIdx.y, n = blockIdx.z, set = n / a.per;
+    const int g_out = chunk / a.cpg4;
+    const int cin_g = a.cin_g, H = a.H, W = a.W, HW = a.H * a.W;
+    const int row_f4 = TAPS * cin_g;
+    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * row_f4;  // float4 per class
+    const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * row_f4;
+    const int ncls = a.has_q ? 2 : 1;
+    for (int e = threadIdx.x; e < ncls * row_f4; e += RQ_THREADS) rq_wsm[e] = __ldg(wq4 + (e / row_f4) * wq_cls + e % row_f4);
+    __syncthreads();
+    const int pos = blockIdx.x * RQ_THREADS + threadIdx.x;
+    if (pos >= HW) return;
+    const int h = pos / W, w = pos % W;
+    const float* xn = a.x + (size_t)n * a.Cin * HW;
+    float RQ[2][4];
+#pragma unroll
+    for (int cls = 0; cls < 2; cls++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) RQ[cls][q] = 0.f;
+        if (cls >= ncls) continue;
+        const float4* ws = rq_wsm + cls * row_f4;
+        for (int jq = 0; jq * CB < cin_g; jq++) {
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cend = min((jq + 1) * CB, cin_g);
+            for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+                const int c1 = min(c0 + 4, cend);
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++) {
+                    const int ph = h + kh - 2;
+                    if (ph < 0 || ph >= H) continue;
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = g_out + 3 + cls - kh - kw;
+                        const int pw = w + kw - 2;
+                        if (gq < 0 || gq >= a.G || pw < 0 || pw >= W) continue;
+                        const float* xp = xn + ((size_t)(gq * cin_g) * H + ph) * W + pw;
+                        const float4* wt = ws + (kh * 5 + kw) * cin_g;
+                        for (int c = c0; c < c1; c++) {
+                            const float xx = __ldg(xp + (size_t)c * HW);
+                            const float4 w4 = wt[c];
+                            u.x = fmaf(xx, w4.x, u.x);
+                            u.y = fmaf(xx, w4.y, u.y);
+                            u.z = fmaf(xx, w4.z, u.z);
+                            u.w = fmaf(xx, w4.w, u.w);
+                        }
+                    }
+                }
+            }
+            RQ[cls][0] = RQ[cls][0] + u.x; RQ[cls][1] = RQ[cls][1] + u.y; RQ[cls][2] = RQ[cls][2] + u.z; RQ[cls][3] = RQ[cls][3] + u.w;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int oc = (chunk % a.cpg4) * 4 + q;
+        if (oc >= a.cout_g) continue;
+        const int o = g_out * a.cout_g + oc;
+        const size_t p = ((size_t)n * a.Cout + o) * HW + pos;
+        float v = ((a.out[p] + RQ[0][q]) + RQ[1][q]) + __ldg(a.bias + set * a.Cout + o);
+        if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
+        if (a.resid) v = v + a.resid[p];
+        a.out[p] = v;
     }
 }
 
@@ -409,6 +431,18 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
     }
     dim3 grid(((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH), (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, a.N);
     cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);
+    static size_t rq_attr = 48 * 1024;
+    if (rq_smem > rq_attr) {
+        e = cudaFuncSetAttribute(cconv_ec_rq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rq_smem);
+        if (e != cudaSuccess) return e;
+        rq_attr = rq_smem;
+    }
+    dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);
+    cconv_ec_rq_kernel<<<grid2, RQ_THREADS, rq_smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }

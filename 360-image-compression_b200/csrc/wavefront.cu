@@ -515,6 +515,157 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
     }
 }
 
+// Chain for single-group nets (the importance stream: G = 1, 144 channels).  A step is ONE anti-diagonal (<= min(H,W)
+// positions) and the same-wavefront taps are the five with kh + kw == 4, all on that diagonal, so per layer
+//   Q[pos][oc] = sum over (16-channel block jq | 4-channel chunk, kh, c) of X[pos + kh][c] * W[oc][kh][c]
+// is a small dense product.  The cluster splits the OUTPUT CHUNKS: CTA r owns chunks [r*kpc, (r+1)*kpc) for all
+// positions, keeps its slice of the next layer's weights in shared memory (cp.async, double buffered, issued a layer
+// ahead), and after each cluster barrier copies the diagonal's activations (one contiguous block of the channel-last
+// frame, written by all CTAs of the cluster) into shared memory once.  Warp task = (chunk, canonical block jq, 32
+// positions): activations are conflict-free float4 reads (row stride cin_g + 4), weights are broadcasts.
+__global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant__ WfNetDev net, int nc, int kpc, int lenp,
+                                                         int cmax) {
+    extern __shared__ float4 wf_sm1[];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    const StepDesc sd = net.steps[*net.ctr];
+    const int par = sd.psum & 1, d = sd.psum, len = sd.len;
+    const int hmin = max(0, d - net.W + 1);
+    const int nqb_max = (cmax + CB - 1) / CB;
+    const int xs = cmax + 4;                                            // padded row stride of the activation tile (floats)
+    float4* wbuf = wf_sm1;                                              // [2][kpc][5][cmax] float4
+    float* xt = reinterpret_cast<float*>(wbuf + (size_t)2 * kpc * 5 * cmax);   // [lenp + 4][xs]
+    float4* part = reinterpret_cast<float4*>(xt + (size_t)(lenp + 4) * xs);   // [kpc][nqb_max][lenp]
+    // slot-0 epilogue item of this thread: (chunk kc0 + it / len, position it % len)
+    WfPre pre;
+    auto stage_weights = [&](int l) {
+        const WfLayerDev& L = net.L[l];
+        if (!L.has_q) return;
+        const int kc0 = rank * kpc, kn = max(0, min(kpc, L.cpg4 - kc0));
+        const int cg = L.cin_g;
+        const float4* src = reinterpret_cast<const float4*>(L.wq) + ((size_t)(net.nsets + n) * L.nchunk + kc0) * TAPS * cg;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + (size_t)(l & 1) * kpc * 5 * cmax);
+        for (int e = tid; e < kn * 5 * cg; e += nt) {
+            const int c = e % cg, kh = (e / cg) % 5, k = e / (5 * cg);
+            cp_async16(dst + 16u * ((k * 5 + kh) * cmax + c), src + ((size_t)k * TAPS + kh * 5 + 4 - kh) * cg + c);
+        }
+    };
+    auto prefetch = [&](int l) {
+        const WfLayerDev& L = net.L[l];
+        const int kc0 = rank * kpc, kn = max(0, min(kpc, L.cpg4 - kc0));
+        if (tid >= kn * len) return;
+        const int kc = kc0 + tid / len, h = hmin + tid % len;
+        pre.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+        const size_t fc = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool live = kc * 4 + q < L.cout_g;
+            pre.bs[q] = live ? __ldg(L.bias + n * L.Cout + kc * 4 + q) : 0.f;
+            pre.sl[q] = live && L.slope ? __ldg(L.slope + n * L.Cout + kc * 4 + q) : 0.f;
+            pre.rs[q] = live && L.rc ? __ldcg(L.rc + fc + q) : 0.f;
+        }
+    };
+    stage_weights(1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    prefetch(0);
+    for (int l = 0; l < WF_LAYERS; l++) {
+        const WfLayerDev& L = net.L[l];
+        const int kc0 = rank * kpc, kn = max(0, min(kpc, L.cpg4 - kc0));
+        if (l >= 1 && l + 1 < WF_LAYERS) {  // weights of layer l+1 (layer 1 was staged before the loop)
+            stage_weights(l + 1);
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        if (L.has_q && kn > 0) {
+            const int cg = L.cin_g;
+            // the diagonal's activations, rows hmin-2 .. hmin+len+1: one contiguous block of the channel-last frame
+            const float4* xsrc = reinterpret_cast<const float4*>(L.xc + wf_fc_index(net.Dp, net.Hp, 1, cg, n, d, 0, hmin - 2));
+            const int row_f4 = cg >> 2;
+            for (int e = tid; e < (len + 4) * row_f4; e += nt) {
+                const int r = e / row_f4, c4 = e % row_f4;
+                *reinterpret_cast<float4*>(xt + (size_t)r * xs + 4 * c4) = __ldcg(xsrc + e);
+            }
+            __syncthreads();
+            const float4* wl = wbuf + (size_t)(l & 1) * kpc * 5 * cmax;
+            const int npg = (len + 31) >> 5, nqb = L.nqb;
+            for (int wt = warp; wt < kn * nqb * npg; wt += nwarps) {
+                const int pg = wt % npg, jq = (wt / npg) % nqb, k = wt / (npg * nqb);
+                const int pos = pg * 32 + lane;
+                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pos < len) {
+                    const int cend = min((jq + 1) * CB, cg);
+                    for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+                        float4 xv[5];
+#pragma unroll
+                        for (int kh = 0; kh < 5; kh++) xv[kh] = *reinterpret_cast<const float4*>(xt + (size_t)(pos + kh) * xs + c0);
+#pragma unroll
+                        for (int kh = 0; kh < 5; kh++) {
+                            const float4* wr = wl + (size_t)(k * 5 + kh) * cmax + c0;
+                            const float x4[4] = {xv[kh].x, xv[kh].y, xv[kh].z, xv[kh].w};
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const float4 w4 = wr[c];
+                                u.x = fmaf(x4[c], w4.x, u.x);
+                                u.y = fmaf(x4[c], w4.y, u.y);
+                                u.z = fmaf(x4[c], w4.z, u.z);
+                                u.w = fmaf(x4[c], w4.w, u.w);
+                            }
+                        }
+                    }
+                    part[((size_t)k * nqb_max + jq) * lenp + pos] = u;
+                }
+            }
+            __syncthreads();
+        }
+        for (int it = tid; it < kn * len; it += nt) {
+            const int k = it / len, pos = it % len, kc = kc0 + k, h = hmin + pos;
+            WfPre p = pre;
+            if (it != tid) {  // further slots (more items than threads): nothing was prefetched
+                p.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+                const size_t fcr = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const bool live = kc * 4 + q < L.cout_g;
+                    p.bs[q] = live ? __ldg(L.bias + n * L.Cout + kc * 4 + q) : 0.f;
+                    p.sl[q] = live && L.slope ? __ldg(L.slope + n * L.Cout + kc * 4 + q) : 0.f;
+                    p.rs[q] = live && L.rc ? __ldcg(L.rc + fcr + q) : 0.f;
+                }
+            }
+            float Q[4] = {0.f, 0.f, 0.f, 0.f};
+            if (L.has_q)
+                for (int j = 0; j < L.nqb; j++) {
+                    const float4 v = part[((size_t)k * nqb_max + j) * lenp + pos];
+                    Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
+                }
+            const float PR[4] = {p.pr.x, p.pr.y, p.pr.z, p.pr.w};
+            const size_t fc = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q] = 0.f;
+                if (kc * 4 + q >= L.cout_g) continue;
+                float y = (PR[q] + Q[q]) + p.bs[q];
+                if (L.slope) y = y > 0.f ? y : y * p.sl[q];
+                if (L.rc) y = y + p.rs[q];
+                v[q] = y;
+                if (L.op) L.op[wf_fp_index(net.D, net.HS, L.Cout, n, kc * 4 + q, d, h)] = y;
+            }
+            if ((L.cout_g & 3) == 0) {
+                *reinterpret_cast<float4*>(L.oc + fc) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (kc * 4 + q < L.cout_g) L.oc[fc + q] = v[q];
+            }
+        }
+        if (l + 1 < WF_LAYERS) {
+            prefetch(l + 1);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            if (nc > 1) cg::this_cluster().sync();
+            else __syncthreads();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -608,12 +759,24 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     e.chain_smem = (size_t)tasks_max * sizeof(float4);
     e.chain4 = G > 1 && G <= 64;
     for (int l = 0; l < WF_LAYERS; l++) e.chain4 = e.chain4 && n.L[l].cpg4 == 1 && (l == 0 || n.L[l].cin_g == 4);
-    if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = false;
+    e.chain1 = G == 1;
+    e.c1_cmax = 4;
+    for (int l = 1; l < WF_LAYERS; l++) { e.chain1 = e.chain1 && (n.L[l].cin_g & 3) == 0; e.c1_cmax = std::max(e.c1_cmax, n.L[l].cin_g); }
+    if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = e.chain1 = false;
     if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
+    if (e.chain1) {
+        e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
+        e.c1_lenp = ((max_len + 31) / 32) * 32;
+        const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)(e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
+                          (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4);
+        if (sm <= 200 * 1024) { e.chain_smem = sm; e.chain_threads = 384; }
+        else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
+    }
     if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
     if (e.chain_smem > chain_attr) {
         LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
         LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
         chain_attr = e.chain_smem;
     }
     return LIC360_OK;
@@ -676,6 +839,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s) {
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
     if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G);
+    if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }
 
