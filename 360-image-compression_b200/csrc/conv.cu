@@ -205,18 +205,38 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
     }
 }
 
-// EC, second pass: one thread = one position x one 4-channel output chunk.  Adds the previous-wavefront (R) and
-// same-wavefront (Q) terms -- every tap reads the cin_g channels of ONE input group -- to the P sums that
-// cconv_ec_kernel left in `out`, then bias / PReLU / residual, in place.  CTA = 256 consecutive positions of one
-// (image, chunk): the chunk's R and Q weights are staged once in shared memory and read as broadcasts; the activation
-// loads are coalesced along w.
+// EC, second pass: adds the previous-wavefront (R) and same-wavefront (Q) terms -- every tap reads the cin_g channels
+// of ONE input group -- to the P sums that cconv_ec_kernel left in `out`, then bias / PReLU / residual, in place.
+// The chunk's R and Q weights are staged once per CTA in shared memory and read as broadcasts; the activation loads are
+// coalesced along w.  Two shapes:
+//   cconv_ec_rq_kernel<CG>  (cin_g <= 16, one canonical block): one thread = one position x one 4-channel output chunk,
+//                           CTA = 256 consecutive positions of one (image, chunk); CG = cin_g when it is 4 (unrolled), else 0
+//   cconv_ec_rqb_kernel     (cin_g > 16): CTA = 32 positions of one (image, chunk); warp (cls, jq) computes the partial
+//                           of canonical block jq, warp 0 combines them in the canonical order.
 constexpr int RQ_THREADS = 256;
 
-__global__ void __launch_bounds__(RQ_THREADS, 3) cconv_ec_rq_kernel(const ConvArgs a) {
+__device__ __forceinline__ void rq_epilogue(const ConvArgs& a, int n, int set, int chunk, int g_out, int pos, const float* R,
+                                            const float* Q) {
+    const int HW = a.H * a.W;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int oc = (chunk % a.cpg4) * 4 + q;
+        if (oc >= a.cout_g) continue;
+        const int o = g_out * a.cout_g + oc;
+        const size_t p = ((size_t)n * a.Cout + o) * HW + pos;
+        float v = ((a.out[p] + R[q]) + Q[q]) + __ldg(a.bias + set * a.Cout + o);
+        if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
+        if (a.resid) v = v + a.resid[p];
+        a.out[p] = v;
+    }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq_kernel(const ConvArgs a) {
     extern __shared__ float4 rq_wsm[];  // [2 classes][TAPS][cin_g]
     const int chunk = blockIdx.y, n = blockIdx.z, set = n / a.per;
     const int g_out = chunk / a.cpg4;
-    const int cin_g = a.cin_g, H = a.H, W = a.W, HW = a.H * a.W;
+    const int cin_g = CG ? CG : a.cin_g, H = a.H, W = a.W, HW = a.H * a.W;
     const int row_f4 = TAPS * cin_g;
     const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * row_f4;  // float4 per class
     const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * row_f4;
@@ -230,15 +250,11 @@ __global__ void __launch_bounds__(RQ_THREADS, 3) cconv_ec_rq_kernel(const ConvAr
     float RQ[2][4];
 #pragma unroll
     for (int cls = 0; cls < 2; cls++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) RQ[cls][q] = 0.f;
-        if (cls >= ncls) continue;
-        const float4* ws = rq_wsm + cls * row_f4;
-        for (int jq = 0; jq * CB < cin_g; jq++) {
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int cend = min((jq + 1) * CB, cin_g);
-            for (int c0 = jq * CB; c0 < cend; c0 += 4) {
-                const int c1 = min(c0 + 4, cend);
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cls < ncls) {
+            const float4* ws = rq_wsm + cls * row_f4;
+            for (int c0 = 0; c0 < cin_g; c0 += 4) {  // canonical 4-channel chunks of the single block
+                const int c1 = min(c0 + 4, cin_g);
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++) {
                     const int ph = h + kh - 2;
@@ -250,31 +266,118 @@ __global__ void __launch_bounds__(RQ_THREADS, 3) cconv_ec_rq_kernel(const ConvAr
                         if (gq < 0 || gq >= a.G || pw < 0 || pw >= W) continue;
                         const float* xp = xn + ((size_t)(gq * cin_g) * H + ph) * W + pw;
                         const float4* wt = ws + (kh * 5 + kw) * cin_g;
-                        for (int c = c0; c < c1; c++) {
-                            const float xx = __ldg(xp + (size_t)c * HW);
-                            const float4 w4 = wt[c];
-                            u.x = fmaf(xx, w4.x, u.x);
-                            u.y = fmaf(xx, w4.y, u.y);
-                            u.z = fmaf(xx, w4.z, u.z);
-                            u.w = fmaf(xx, w4.w, u.w);
+                        if (CG == 4) {
+                            float xx[4];
+#pragma unroll
+                            for (int c = 0; c < 4; c++) xx[c] = __ldg(xp + (size_t)c * HW);
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const float4 w4 = wt[c];
+                                u.x = fmaf(xx[c], w4.x, u.x);
+                                u.y = fmaf(xx[c], w4.y, u.y);
+                                u.z = fmaf(xx[c], w4.z, u.z);
+                                u.w = fmaf(xx[c], w4.w, u.w);
+                            }
+                        } else {
+                            for (int c = c0; c < c1; c++) {
+                                const float xx = __ldg(xp + (size_t)c * HW);
+                                const float4 w4 = wt[c];
+                                u.x = fmaf(xx, w4.x, u.x);
+                                u.y = fmaf(xx, w4.y, u.y);
+                                u.z = fmaf(xx, w4.z, u.z);
+                                u.w = fmaf(xx, w4.w, u.w);
+                            }
                         }
                     }
                 }
             }
-            RQ[cls][0] = RQ[cls][0] + u.x; RQ[cls][1] = RQ[cls][1] + u.y; RQ[cls][2] = RQ[cls][2] + u.z; RQ[cls][3] = RQ[cls][3] + u.w;
+        }
+        RQ[cls][0] = 0.f + u.x; RQ[cls][1] = 0.f + u.y; RQ[cls][2] = 0.f + u.z; RQ[cls][3] = 0.f + u.w;
+    }
+    rq_epilogue(a, n, set, chunk, g_out, pos, RQ[0], RQ[1]);
+}
+
+__global__ void __launch_bounds__(640, 2) cconv_ec_rqb_kernel(const ConvArgs a, int nqb, int tap_cap) {
+    extern __shared__ float4 rq_wsm[];  // [2 classes][tap_cap][cin_g] weights of the taps that select a valid group, then partials
+    __shared__ int s_tap[2][TAPS], s_ntap[2];
+    const int chunk = blockIdx.y, n = blockIdx.z, set = n / a.per;
+    const int g_out = chunk / a.cpg4;
+    const int cin_g = a.cin_g, H = a.H, W = a.W, HW = a.H * a.W;
+    const int row_f4 = TAPS * cin_g;
+    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * row_f4;
+    const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * row_f4;
+    const int ncls = a.has_q ? 2 : 1;
+    const int lane = threadIdx.x, wid = threadIdx.y, tid = wid * 32 + lane, nthr = blockDim.x * blockDim.y;
+    float4* part = rq_wsm + 2 * tap_cap * cin_g;
+    if (tid < 2) {  // taps of class tid whose selected input group exists, in canonical (kh, kw) order
+        int m = 0;
+        for (int t = 0; t < TAPS; t++) {
+            const int gq = g_out + 3 + tid - t / 5 - t % 5;
+            if (gq >= 0 && gq < a.G && tid < ncls) s_tap[tid][m++] = t;
+        }
+        s_ntap[tid] = m;
+    }
+    __syncthreads();
+    for (int c = 0; c < ncls; c++)
+        for (int e = tid; e < s_ntap[c] * cin_g; e += nthr)
+            rq_wsm[c * tap_cap * cin_g + e] = __ldg(wq4 + c * wq_cls + (size_t)s_tap[c][e / cin_g] * cin_g + e % cin_g);
+    __syncthreads();
+    const int pos = blockIdx.x * 32 + lane;
+    const bool valid = pos < HW;
+    const int h = pos / W, w = pos % W;
+    const int cls = wid / nqb, jq = wid % nqb;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && cls < ncls) {
+        const float* xn = a.x + (size_t)n * a.Cin * HW;
+        const float4* ws = rq_wsm + cls * tap_cap * cin_g;
+        const int cend = min((jq + 1) * CB, cin_g), nt = s_ntap[cls];
+        for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+            const int c1 = min(c0 + 4, cend);
+            for (int ti = 0; ti < nt; ti++) {
+                const int t = s_tap[cls][ti], kh = t / 5, kw = t % 5;
+                const int ph = h + kh - 2, pw = w + kw - 2;
+                if (ph < 0 || ph >= H || pw < 0 || pw >= W) continue;
+                const int gq = g_out + 3 + cls - kh - kw;
+                const float* xp = xn + ((size_t)(gq * cin_g) * H + ph) * W + pw;
+                const float4* wt = ws + ti * cin_g;
+                if (c1 - c0 == 4) {
+                    float xx[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) xx[c] = __ldg(xp + (size_t)(c0 + c) * HW);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 w4 = wt[c0 + c];
+                        u.x = fmaf(xx[c], w4.x, u.x);
+                        u.y = fmaf(xx[c], w4.y, u.y);
+                        u.z = fmaf(xx[c], w4.z, u.z);
+                        u.w = fmaf(xx[c], w4.w, u.w);
+                    }
+                } else {
+                    for (int c = c0; c < c1; c++) {
+                        const float xx = __ldg(xp + (size_t)c * HW);
+                        const float4 w4 = wt[c];
+                        u.x = fmaf(xx, w4.x, u.x);
+                        u.y = fmaf(xx, w4.y, u.y);
+                        u.z = fmaf(xx, w4.z, u.z);
+                        u.w = fmaf(xx, w4.w, u.w);
+                    }
+                }
+            }
         }
     }
+    part[wid * 32 + lane] = u;
+    __syncthreads();
+    if (wid != 0 || !valid) return;
+    float RQ[2][4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int oc = (chunk % a.cpg4) * 4 + q;
-        if (oc >= a.cout_g) continue;
-        const int o = g_out * a.cout_g + oc;
-        const size_t p = ((size_t)n * a.Cout + o) * HW + pos;
-        float v = ((a.out[p] + RQ[0][q]) + RQ[1][q]) + __ldg(a.bias + set * a.Cout + o);
-        if (a.slope) { const float sl = __ldg(a.slope + set * a.Cout + o); v = v > 0.f ? v : v * sl; }
-        if (a.resid) v = v + a.resid[p];
-        a.out[p] = v;
+    for (int c = 0; c < 2; c++) {
+        RQ[c][0] = RQ[c][1] = RQ[c][2] = RQ[c][3] = 0.f;
+        for (int j = 0; j < nqb; j++) {
+            const float4 v = part[(c * nqb + j) * 32 + lane];
+            RQ[c][0] = RQ[c][0] + v.x; RQ[c][1] = RQ[c][1] + v.y; RQ[c][2] = RQ[c][2] + v.z; RQ[c][3] = RQ[c][3] + v.w;
+        }
     }
+    rq_epilogue(a, n, set, chunk, g_out, pos, RQ[0], RQ[1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -434,15 +537,31 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);
-    static size_t rq_attr = 48 * 1024;
-    if (rq_smem > rq_attr) {
-        e = cudaFuncSetAttribute(cconv_ec_rq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rq_smem);
-        if (e != cudaSuccess) return e;
-        rq_attr = rq_smem;
+    const int nqb = (a.cin_g + CB - 1) / CB;
+    if (nqb == 1) {
+        const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);  // <= 12.8 KB
+        dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);
+        if (a.cin_g == 4) cconv_ec_rq_kernel<4><<<grid2, RQ_THREADS, rq_smem, s>>>(a);
+        else cconv_ec_rq_kernel<0><<<grid2, RQ_THREADS, rq_smem, s>>>(a);
+    } else {
+        if (2 * nqb > 20) return cudaErrorInvalidConfiguration;  // cin_g <= 160
+        int tap_cap = 0;  // most taps of one class that select an existing input group, over all output groups
+        for (int g = 0; g < a.G; g++)
+            for (int cls = 0; cls < 2; cls++) {
+                int m = 0;
+                for (int t = 0; t < TAPS; t++) { const int gq = g + 3 + cls - t / 5 - t % 5; m += gq >= 0 && gq < a.G; }
+                tap_cap = std::max(tap_cap, m);
+            }
+        const size_t rq_smem = ((size_t)2 * tap_cap * a.cin_g + (size_t)2 * nqb * 32) * sizeof(float4);
+        static size_t rq_attr = 48 * 1024;
+        if (rq_smem > rq_attr) {
+            e = cudaFuncSetAttribute(cconv_ec_rqb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rq_smem);
+            if (e != cudaSuccess) return e;
+            rq_attr = rq_smem;
+        }
+        dim3 grid2((a.H * a.W + 31) / 32, a.nchunk, a.N), block2(32, 2 * nqb);
+        cconv_ec_rqb_kernel<<<grid2, block2, rq_smem, s>>>(a, nqb, tap_cap);
     }
-    dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);
-    cconv_ec_rq_kernel<<<grid2, RQ_THREADS, rq_smem, s>>>(a);
     g_launches++;
     return cudaGetLastError();
 }

@@ -746,7 +746,12 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         old_attr = e.old_smem;
     }
     e.cluster = 8;
-    if (const char* s = getenv("LIC360_WF_CLUSTER")) e.cluster = std::max(1, std::min(8, atoi(s)));
+    if (const char* s = getenv("LIC360_WF_CLUSTER")) e.cluster = std::max(1, std::min(16, atoi(s)));
+    if (e.cluster > 8) {  // non-portable cluster size (16 CTAs): opt in per kernel
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     int items_max = 0, tasks_max = 0;
     for (int l = 0; l < WF_LAYERS; l++) {
         const int per = (max_len * n.L[l].cpg4 + e.cluster - 1) / e.cluster;
