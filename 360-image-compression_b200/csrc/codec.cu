@@ -216,25 +216,39 @@ __device__ __forceinline__ void rows_done(int* done, volatile int* flag, int ste
     }
 }
 
-// decoder: CDF rows of the slab of step *ctr from the engine's last frame (channel-last, 3 nets x G*3 channels)
+// decoder: CDF rows of the slab of step *ctr from the engine's last frame (group-major channel-last, 3 nets x G x 3).
+// 8 lanes per symbol: lane j computes bin j (the 21 erff of a row are the critical path of this latency-bound kernel),
+// lane 0 gathers the bins, runs the monotonic fix-up and stores the packed 16-byte row.
 __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __restrict__ mask, const int32_t* __restrict__ idx,
                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
                                    int G, int H, int W, int Dp, int Hp, float s2, int* done, int* flag) {
     const int step = *ctr;
     const StepDesc d = steps[step];
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l < d.len) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = gt >> 3, j = gt & 7;
+    const bool live = l < d.len;
+    float bin = 0.f;
+    int th = 0, tw = 0, tc = 0;
+    if (live) {
         const int HW = H * W;
-        const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
-        const int tc = d.psum - th - tw;
-        float wv[3], dv[3], mv[3], o[9];
+        th = __ldg(idx + d.start + l); tw = __ldg(idx + d.start + l + HW);
+        tc = d.psum - th - tw;
+        float wv[3], dv[3], mv[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             wv[i] = y[wf_fc_index(Dp, Hp, G, 3, 0, th + tw, tc, th) + i];
             dv[i] = y[wf_fc_index(Dp, Hp, G, 3, 1, th + tw, tc, th) + i];
             mv[i] = y[wf_fc_index(Dp, Hp, G, 3, 2, th + tw, tc, th) + i];
         }
-        gmm_row(wv, dv, mv, o, 3, 8, 3.5f, 65536.f, 1e-6f, s2);
+        gmm_prep(wv, dv, 3, 1e-6f);
+        if (j >= 1) bin = gmm_bin_value(wv, dv, mv, j, 3, 3.5f, 65536.f, s2);
+    }
+    float o[9];
+    o[0] = 0.f; o[8] = 65536.f;
+#pragma unroll
+    for (int k = 1; k < 8; k++) o[k] = __shfl_sync(0xffffffffu, bin, (threadIdx.x & 24) + k);
+    if (live && j == 0) {
+        fixup_row(o, 8, true);
         const size_t pos = ((size_t)tc * H + th) * W + tw;
         pack_gmm_row(o, 0, mask[pos] < 0.5f ? 0 : 1, rows + (size_t)l * 8);
     }
@@ -388,7 +402,7 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
     if (is_code)
-        gmm_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], c->mask192_dev /* = mask_up, set before the first step */, n.idx_dev,
+        gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, s>>>(n.wf.fc[12], c->mask192_dev /* = mask_up, set before the first step */, n.idx_dev,
                                                  n.steps_dev, c->ctr_dev, c->rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
                                                  (float)(1. / sqrt(2.0)), c->done_dev, c->flag_host);
     else

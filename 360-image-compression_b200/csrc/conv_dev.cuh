@@ -28,25 +28,42 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // band cell of position `lane`, tap (kh,kw): band[ch*DC_BAND + (lane+kh)*RS + (kh+kw)*CS]
 //   NCHW kernel  : rows = image rows, 9 columns         -> RS = 9, CS = 1,  CHS = 324
 //   skewed kernel: rows = diagonals (kh+kw), 40 columns -> RS = 1, CS = 40, CHS = 360 (TMA box, wavefront.cu)
+// taps with kh + kw < NS, fully unrolled with compile-time tap predicates (no per-tap compare/branch at run time)
+template <int RS, int CS, int NS>
+__device__ __forceinline__ void dc_taps_fma(const float* bw, const float4* wrow, float4& u) {
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            if (kh + kw >= NS) continue;
+            const float xx = bw[kh * RS + (kh + kw) * CS];
+            const float4 w4 = wrow[kh * 5 + kw];
+            u.x = fmaf(xx, w4.x, u.x);
+            u.y = fmaf(xx, w4.y, u.y);
+            u.z = fmaf(xx, w4.z, u.z);
+            u.w = fmaf(xx, w4.w, u.w);
+        }
+    }
+}
+
 template <int RS, int CS, int CHS>
 __device__ __forceinline__ void dc_stage_fma(const float* band, const float4* wsm, int nc, int lane, int chan0, int cin_g,
                                              int tc, float4& u) {
     for (int ch = 0; ch < nc; ch++) {
         const float* bw = band + ch * CHS + lane * RS;
         const float4* wrow = wsm + ch * TAPS;
-        const int bound = tc + 3 - (chan0 + ch) / cin_g;
-#pragma unroll
-        for (int kh = 0; kh < 5; kh++) {
-#pragma unroll
-            for (int kw = 0; kw < 5; kw++) {
-                if (kh + kw >= bound) continue;
-                const float xx = bw[kh * RS + (kh + kw) * CS];
-                const float4 w4 = wrow[kh * 5 + kw];
-                u.x = fmaf(xx, w4.x, u.x);
-                u.y = fmaf(xx, w4.y, u.y);
-                u.z = fmaf(xx, w4.z, u.z);
-                u.w = fmaf(xx, w4.w, u.w);
-            }
+        const int bound = tc + 3 - (chan0 + ch) / cin_g;  // warp-uniform
+        if (bound >= 9) { dc_taps_fma<RS, CS, 9>(bw, wrow, u); continue; }
+        switch (bound) {
+            case 8: dc_taps_fma<RS, CS, 8>(bw, wrow, u); break;
+            case 7: dc_taps_fma<RS, CS, 7>(bw, wrow, u); break;
+            case 6: dc_taps_fma<RS, CS, 6>(bw, wrow, u); break;
+            case 5: dc_taps_fma<RS, CS, 5>(bw, wrow, u); break;
+            case 4: dc_taps_fma<RS, CS, 4>(bw, wrow, u); break;
+            case 3: dc_taps_fma<RS, CS, 3>(bw, wrow, u); break;
+            case 2: dc_taps_fma<RS, CS, 2>(bw, wrow, u); break;
+            case 1: dc_taps_fma<RS, CS, 1>(bw, wrow, u); break;
+            default: break;
         }
     }
 }

@@ -23,27 +23,37 @@ __device__ __forceinline__ void fixup_row(float* o, int ngroup, bool gmm_rule) {
         for (int i = midx; i < ngroup; i++) o[i + 1] -= bias;
 }
 
-// GMM row: wv/dv/mv hold the raw mixture logits / deltas / means on entry; on exit wv = softmax, dv = clamped delta
-// (what the reference writes back in place); o receives nstep+1 bins.
-__device__ __forceinline__ void gmm_row(float* wv, float* dv, const float* mv, float* o, int ng, int nstep, float bias,
-                                        float total, float beta, float s2) {
-    const int nt = nstep + 1;
+// GMM row, part 1: wv = softmax of the mixture logits, dv = clamped delta, in place (what the reference writes back,
+// entropy_gmm_table_cuda.cu:29-57)
+__device__ __forceinline__ void gmm_prep(float* wv, float* dv, int ng, float beta) {
     float mval = wv[0], psum = 0.f;
     for (int i = 1; i < ng; i++) if (mval < wv[i]) mval = wv[i];
     for (int i = 0; i < ng; i++) { wv[i] = expf(wv[i] - mval); psum += wv[i]; }
     for (int i = 0; i < ng; i++) wv[i] = wv[i] / psum;
     for (int i = 0; i < ng; i++) { float t = dv[i]; dv[i] = t < 0 ? beta : t + beta; }
+}
+
+// GMM row, part 2: bin pt (1 <= pt <= nstep-1) from the prepared parameters (entropy_gmm_table_cuda.cu:60-83)
+__device__ __forceinline__ float gmm_bin_value(const float* wv, const float* dv, const float* mv, int pt, int ng, float bias, float total,
+                                               float s2) {
+    float v = pt - 1 - bias + 0.5;  // (float)(pt-1) - bias in float, + 0.5 in double, rounded to float
+    float ps = 0, f;
+    for (int i = 0; i < ng; i++) {
+        f = 0.5 + 0.5 * erff(s2 * (v - mv[i]) / dv[i]);  // erff in float; 0.5+0.5*(.) in double -> float
+        ps = ps + wv[i] * f;                              // float, contracted to FFMA as in the reference
+    }
+    return static_cast<int>(total * ps + 0.5);  // float product, + 0.5 in double, truncation
+}
+
+// GMM row: wv/dv/mv hold the raw mixture logits / deltas / means on entry; on exit wv = softmax, dv = clamped delta
+// (what the reference writes back in place); o receives nstep+1 bins.
+__device__ __forceinline__ void gmm_row(float* wv, float* dv, const float* mv, float* o, int ng, int nstep, float bias,
+                                        float total, float beta, float s2) {
+    const int nt = nstep + 1;
+    gmm_prep(wv, dv, ng, beta);
     o[0] = 0.f;
     o[nt - 1] = static_cast<int>(total);
-    for (int pt = 1; pt < nt - 1; pt++) {
-        float v = pt - 1 - bias + 0.5;  // (float)(pt-1) - bias in float, + 0.5 in double, rounded to float
-        float ps = 0, f;
-        for (int i = 0; i < ng; i++) {
-            f = 0.5 + 0.5 * erff(s2 * (v - mv[i]) / dv[i]);  // erff in float; 0.5+0.5*(.) in double -> float
-            ps = ps + wv[i] * f;                              // float, contracted to FFMA as in the reference
-        }
-        o[pt] = static_cast<int>(total * ps + 0.5);  // float product, + 0.5 in double, truncation
-    }
+    for (int pt = 1; pt < nt - 1; pt++) o[pt] = gmm_bin_value(wv, dv, mv, pt, ng, bias, total, s2);
     fixup_row(o, nstep, true);
 }
 

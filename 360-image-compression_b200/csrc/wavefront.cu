@@ -264,26 +264,120 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
     return u;
 }
 
-// previous-wavefront terms of ALL layers of step *ctr: pbuf <- P + R.  Same CTA geometry as wf_old_kernel; warp jq =
-// canonical 16-channel block jq of the group.
+// previous-wavefront terms of ALL layers of step *ctr: pbuf <- P + R.  Same CTA geometry as wf_old_kernel, so a CTA
+// has ONE output group: its row of class-0 weights ([tap][cin_g] float4, only the taps that select an existing group)
+// is staged in shared memory with cp.async; warp jq = canonical 16-channel block jq of the group, and the activation
+// loads of a whole 4-channel chunk (all taps) are in flight before its first FMA.
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant__ WfNetDev net) {
-    extern __shared__ float4 wf_part[];
+__global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant__ WfNetDev net, int wcap) {
+    extern __shared__ float4 wf_psm[];  // [TAPS * cin_g (<= wcap)] weights, then [nqb][32] partials
     const WfTile t = wf_tile(net, 0);
     if (!t.ok) return;
     const WfLayerDev& L = net.L[t.l];
-    const int lane = threadIdx.x, jq = threadIdx.y;
+    const int lane = threadIdx.x, jq = threadIdx.y, tid = jq * 32 + lane, nthr = blockDim.x * blockDim.y;
+    const int cin_g = L.cin_g, G = net.G, Hp = net.Hp;
+    const int gsel0 = t.tc + 3;
+    {
+        const float4* src = reinterpret_cast<const float4*>(L.wq) + ((size_t)t.n * L.nchunk + t.tc * L.cpg4 + t.kc) * TAPS * cin_g;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(wf_psm);
+        for (int e = tid; e < TAPS * cin_g; e += nthr) {
+            const int tap = e / cin_g, gq = gsel0 - tap / 5 - tap % 5;
+            if (gq >= 0 && gq < G) cp_async16(dst + 16u * e, src + e);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    float4* part = wf_psm + wcap;
     const int h = t.hbase + lane;
     const bool valid = h <= t.hmax;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (jq < L.nqb && valid) r = wf_rq_partial<false>(net, L, t.n, t.d, h, t.tc, t.kc, jq, 0);
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (jq < L.nqb && valid) {
+        const int cend = min((jq + 1) * CB, cin_g);
+        const float* xb = L.xc + (((size_t)t.n * net.Dp + t.d) * G * Hp + h) * cin_g;
+        if ((cin_g & 3) == 0 && G == 1) {
+            // one group: exactly the taps with kh + kw == gsel0 (== 3) contribute; all chunks of the block in flight
+            float4 xv[4][5];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++) {
+                    const int kw = gsel0 - kh, c0 = jq * CB + 4 * q;
+                    xv[q][kh] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kw >= 0 && kw < 5 && c0 < cend) xv[q][kh] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gsel0 * Hp + kh) * cin_g + c0));
+                }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c0 = jq * CB + 4 * q;
+                if (c0 >= cend) break;
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++) {
+                    const int kw = gsel0 - kh;
+                    if (kw < 0 || kw >= 5) continue;
+                    const float xs[4] = {xv[q][kh].x, xv[q][kh].y, xv[q][kh].z, xv[q][kh].w};
+                    const float4* wt = wf_psm + (kh * 5 + kw) * cin_g + c0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 w4 = wt[c];
+                        u.x = fmaf(xs[c], w4.x, u.x); u.y = fmaf(xs[c], w4.y, u.y); u.z = fmaf(xs[c], w4.z, u.z); u.w = fmaf(xs[c], w4.w, u.w);
+                    }
+                }
+            }
+        } else if ((cin_g & 3) == 0) {
+            for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+                float4 xv[TAPS];
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = gsel0 - kh - kw;
+                        xv[kh * 5 + kw] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (gq >= 0 && gq < G)
+                            xv[kh * 5 + kw] = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0));
+                    }
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = gsel0 - kh - kw;
+                        if (gq < 0 || gq >= G) continue;
+                        const float4 x4 = xv[kh * 5 + kw];
+                        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                        const float4* wt = wf_psm + (kh * 5 + kw) * cin_g + c0;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const float4 w4 = wt[c];
+                            u.x = fmaf(xs[c], w4.x, u.x); u.y = fmaf(xs[c], w4.y, u.y); u.z = fmaf(xs[c], w4.z, u.z); u.w = fmaf(xs[c], w4.w, u.w);
+                        }
+                    }
+            }
+        } else {
+            for (int c0 = jq * CB; c0 < cend; c0 += 4) {
+                const int nc = min(4, cend - c0);
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        const int gq = gsel0 - kh - kw;
+                        if (gq < 0 || gq >= G) continue;
+                        const float* xp = xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0;
+                        const float4* wt = wf_psm + (kh * 5 + kw) * cin_g + c0;
+                        for (int c = 0; c < nc; c++) {
+                            const float xx = __ldg(xp + c);
+                            const float4 w4 = wt[c];
+                            u.x = fmaf(xx, w4.x, u.x); u.y = fmaf(xx, w4.y, u.y); u.z = fmaf(xx, w4.z, u.z); u.w = fmaf(xx, w4.w, u.w);
+                        }
+                    }
+            }
+        }
+    }
+    float4 r = u;
     if (blockDim.y > 1) {
-        wf_part[jq * 32 + lane] = r;
+        part[jq * 32 + lane] = u;
         __syncthreads();
         if (jq != 0) return;
         r = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < L.nqb; j++) {
-            const float4 v = wf_part[j * 32 + lane];
+            const float4 v = part[j * 32 + lane];
             r.x = r.x + v.x; r.y = r.y + v.y; r.z = r.z + v.z; r.w = r.w + v.w;
         }
     } else {
@@ -738,51 +832,75 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     }
     // launch shapes
     e.old_smem = 128 + (size_t)WF_OLD_WARPS * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
-    e.prev_smem = (size_t)e.nqb_max * 32 * sizeof(float4);
+    e.prev_wcap = 0;
+    for (int l = 0; l < WF_LAYERS; l++) e.prev_wcap = std::max(e.prev_wcap, TAPS * n.L[l].cin_g);
+    e.prev_smem = ((size_t)e.prev_wcap + (size_t)e.nqb_max * 32) * sizeof(float4);
+    static size_t prev_attr = 48 * 1024;
+    if (e.prev_smem > prev_attr) {
+        LIC360_CUDA(cudaFuncSetAttribute(wf_prev_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.prev_smem));
+        LIC360_CUDA(cudaFuncSetAttribute(wf_prev_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.prev_smem));
+        prev_attr = e.prev_smem;
+    }
     // the attribute is per kernel, not per engine: only ever raise it (two engines with different channel counts share it)
     static size_t old_attr = 48 * 1024, chain_attr = 48 * 1024;
     if (e.old_smem > old_attr) {
         LIC360_CUDA(cudaFuncSetAttribute(wf_old_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old_smem));
         old_attr = e.old_smem;
     }
-    e.cluster = 8;
-    if (const char* s = getenv("LIC360_WF_CLUSTER")) e.cluster = std::max(1, std::min(16, atoi(s)));
-    if (e.cluster > 8) {  // non-portable cluster size (16 CTAs): opt in per kernel
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
-    int items_max = 0, tasks_max = 0;
-    for (int l = 0; l < WF_LAYERS; l++) {
-        const int per = (max_len * n.L[l].cpg4 + e.cluster - 1) / e.cluster;
-        items_max = std::max(items_max, per);
-        tasks_max = std::max(tasks_max, per * (n.L[l].has_q ? n.L[l].nqb : 1));
-    }
-    // a kernel row of an item (5 activations + 20 weight vectors) is kept in registers: at most 384 threads per CTA
-    // (168 registers each); CTAs with more tasks loop
-    e.chain_threads = std::min(384, std::max(128, ((tasks_max + 31) / 32) * 32));
-    e.chain_smem = (size_t)tasks_max * sizeof(float4);
-    e.chain4 = G > 1 && G <= 64;
-    for (int l = 0; l < WF_LAYERS; l++) e.chain4 = e.chain4 && n.L[l].cpg4 == 1 && (l == 0 || n.L[l].cin_g == 4);
-    e.chain1 = G == 1;
-    e.c1_cmax = 4;
-    for (int l = 1; l < WF_LAYERS; l++) { e.chain1 = e.chain1 && (n.L[l].cin_g & 3) == 0; e.c1_cmax = std::max(e.c1_cmax, n.L[l].cin_g); }
-    if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = e.chain1 = false;
-    if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
-    if (e.chain1) {
-        e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
-        e.c1_lenp = ((max_len + 31) / 32) * 32;
-        const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)(e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
-                          (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4);
-        if (sm <= 200 * 1024) { e.chain_smem = sm; e.chain_threads = 384; }
-        else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
-    }
-    if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
-    if (e.chain_smem > chain_attr) {
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-        LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-        chain_attr = e.chain_smem;
+    // chain kernels: one cluster per net.  16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
+    // else the portable maximum of 8.
+    LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    int want = 16;
+    if (const char* s = getenv("LIC360_WF_CLUSTER")) want = std::max(1, std::min(16, atoi(s)));
+    for (e.cluster = want;; e.cluster = 8) {
+        int tasks_max = 0;
+        for (int l = 0; l < WF_LAYERS; l++) {
+            const int per = (max_len * n.L[l].cpg4 + e.cluster - 1) / e.cluster;
+            tasks_max = std::max(tasks_max, per * (n.L[l].has_q ? n.L[l].nqb : 1));
+        }
+        // a kernel row of an item (5 activations + 20 weight vectors) is kept in registers: at most 384 threads per CTA
+        // (168 registers each); CTAs with more tasks loop
+        e.chain_threads = std::min(384, std::max(128, ((tasks_max + 31) / 32) * 32));
+        e.chain_smem = (size_t)tasks_max * sizeof(float4);
+        e.chain4 = G > 1 && G <= 64;
+        for (int l = 0; l < WF_LAYERS; l++) e.chain4 = e.chain4 && n.L[l].cpg4 == 1 && (l == 0 || n.L[l].cin_g == 4);
+        e.chain1 = G == 1;
+        e.c1_cmax = 4;
+        for (int l = 1; l < WF_LAYERS; l++) { e.chain1 = e.chain1 && (n.L[l].cin_g & 3) == 0; e.c1_cmax = std::max(e.c1_cmax, n.L[l].cin_g); }
+        if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = e.chain1 = false;
+        if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
+        if (e.chain1) {
+            e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
+            e.c1_lenp = ((max_len + 31) / 32) * 32;
+            const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)(e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
+                              (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4);
+            if (sm <= 200 * 1024) { e.chain_smem = sm; e.chain_threads = 384; }
+            else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
+        }
+        if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
+        if (e.chain_smem > chain_attr) {
+            LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+            LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+            LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
+            chain_attr = e.chain_smem;
+        }
+        if (e.cluster <= 8) break;
+        // can nsets clusters of this size be resident at once?
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(nsets * e.cluster); cfg.blockDim = dim3(e.chain_threads); cfg.dynamicSmemBytes = e.chain_smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = e.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t r = e.chain4 ? cudaOccupancyMaxActiveClusters(&nclusters, wf_chain4_kernel, &cfg)
+                      : e.chain1 ? cudaOccupancyMaxActiveClusters(&nclusters, wf_chain1_kernel, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&nclusters, wf_chain_kernel<384>, &cfg);
+        if (r == cudaSuccess && nclusters >= nsets) break;
+        cudaGetLastError();
     }
     return LIC360_OK;
 }
@@ -823,8 +941,8 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s) {
 cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s) {
     const WfNetDev& n = e.dev;
     dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, e.nqb_max);
-    if (e.nqb_max <= 10) wf_prev_kernel<320><<<grid, block, e.prev_smem, s>>>(n);
-    else wf_prev_kernel<1024><<<grid, block, e.prev_smem, s>>>(n);
+    if (e.nqb_max <= 10) wf_prev_kernel<320><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap);
+    else wf_prev_kernel<1024><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap);
     g_launches++;
     return cudaGetLastError();
 }
