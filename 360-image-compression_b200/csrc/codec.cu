@@ -367,10 +367,9 @@ static int check_params(const NetDesc& n) {
     return LIC360_OK;
 }
 
-// the kernels of one decode step in stream order.  The old terms of the NEXT step come last: the host is released by
-// the flag that the rows kernel raises, so this launch (the bulk of the arithmetic) overlaps the host arithmetic decoder.
-// (A parallel graph branch does not help: the chain kernel's clusters need whole SMs and would wait for this kernel's
-// CTAs to drain anyway.)
+// the kernels of one decode step.  side == s (serialized / profile mode): everything in stream order, the old terms of
+// the NEXT step last.  side != s (graph capture): the old terms run on a parallel low-priority branch; either way the
+// host is released by the flag that the rows kernel raises, so the bulk of the arithmetic also overlaps the host coder.
 // ev != nullptr: profile mode, events bracket the kernel classes (everything on `s`).
 #define WF_DEBUG_SYNC(what)                                                                               \
     do {                                                                                                \
@@ -394,6 +393,16 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("scatter kernel");
+    const bool fork = side != s;
+    if (fork) {
+        // parallel graph branch, forked AFTER the scatter (the old terms of step p+1 read the symbols of wavefront p-1 it
+        // just wrote) and joined before the counter advances.  The branch runs at the lowest priority: the block scheduler
+        // stops feeding it while the chain's clusters are waiting for SMs, and it fills the SMs the chain leaves idle.
+        LIC360_CUDA(cudaEventRecord(c->ev_fork, s));
+        LIC360_CUDA(cudaStreamWaitEvent(side, c->ev_fork, 0));
+        LIC360_CUDA(wf_launch_old(n.wf, 1, side));
+        LIC360_CUDA(cudaEventRecord(c->ev_join, side));
+    }
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
     LIC360_CUDA(wf_launch_prev(n.wf, s));
     WF_DEBUG_SYNC("previous-wavefront kernel");
@@ -411,8 +420,8 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
-    (void)side;
-    LIC360_CUDA(wf_launch_old(n.wf, 1, s));
+    if (fork) LIC360_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    else LIC360_CUDA(wf_launch_old(n.wf, 1, s));
     WF_DEBUG_SYNC("old-term kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
     advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);
@@ -427,12 +436,32 @@ static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaGraph_t g;
     const long long l0 = g_launches;
     LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = launch_step(c, n, is_code, s, c->side, nullptr);
+    static const bool overlap = getenv("LIC360_WF_OVERLAP") != nullptr;  // measured slower on B200 (the branch delays the chain clusters): off by default
+    const int rc = launch_step(c, n, is_code, s, overlap ? c->side : s, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &g);
     n.graph_nodes = (int)(g_launches - l0);
     g_launches = l0;  // captured, not launched: replays are counted in decode_stream
     if (rc != LIC360_OK) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
     LIC360_CUDA(e);
+    {   // kernel-node priorities: old-term kernel lowest, everything on the critical path highest
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        size_t nn = 0;
+        LIC360_CUDA(cudaGraphGetNodes(g, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        LIC360_CUDA(cudaGraphGetNodes(g, nodes.data(), &nn));
+        for (size_t i = 0; i < nn; i++) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp;
+            if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+            cudaKernelNodeAttrValue v;
+            memset(&v, 0, sizeof(v));
+            v.priority = kp.func == wf_old_kernel_ptr() ? prio_lo : prio_hi;
+            cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v);
+        }
+        cudaGetLastError();
+    }
     LIC360_CUDA(cudaGraphInstantiate(&n.graph, g, 0));
     cudaGraphDestroy(g);
     return LIC360_OK;

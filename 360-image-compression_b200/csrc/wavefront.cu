@@ -905,6 +905,8 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     return LIC360_OK;
 }
 
+const void* wf_old_kernel_ptr() { return reinterpret_cast<const void*>(&wf_old_kernel); }
+
 void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope) {
     WfLayerDev& L = e.dev.L[l];
     L.wp = wp; L.wq = wq; L.bias = bias; L.slope = slope;
