@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(256) quant_fwd_kernel(const float* __restrict_
                     yv[k] = xv[k] - tmp;
                 }
                 qv[k] = (float)j;
-                atomicAdd(&shist[j], 1);
+                // warp-aggregated histogram update: one shared-memory atomic per distinct level in the warp
+                const unsigned act = __activemask();
+                const unsigned same = __match_any_sync(act, j);
+                if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&shist[j], __popc(same));
             }
             if (V == 4) {
                 *reinterpret_cast<float4*>(y + base + e) = make_float4(yv[0], yv[1], yv[2], yv[3]);
@@ -367,15 +370,25 @@ __device__ __forceinline__ void sphere_src(int ph, int pw, int H, int W, int pad
     if (th < 0 || th >= H) { th = (2 * H - 1 - th) % H; tw = (2 * W - 1 - tw) % W; }
 }
 
-__global__ void sphere_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H, int W, int pad) {
+// one warp per OUTPUT row (8 rows per CTA): the row's source row / pole flip is decided once, the lanes walk the
+// columns with 32-bit arithmetic only, loads and stores are contiguous
+constexpr int ROWS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(32 * ROWS_PER_CTA) sphere_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H,
+                                                                     int W, int pad) {
     const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-    const size_t total = (size_t)NC * Ho * Wo;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int pw = (int)(i % Wo), ph = (int)((i / Wo) % Ho);
-        const size_t n = i / ((size_t)Wo * Ho);
-        int th, tw;
-        sphere_src(ph, pw, H, W, pad, th, tw);
-        out[i] = in[(n * H + th) * W + tw];
+    const int row = blockIdx.x * ROWS_PER_CTA + threadIdx.y;
+    if (row >= NC * Ho) return;
+    const int n = row / Ho, ph = row % Ho;
+    int th = ph - pad;
+    const bool flip = th < 0 || th >= H;
+    if (flip) th = (2 * H - 1 - th) % H;
+    const float* src = in + ((size_t)n * H + th) * W;
+    float* dst = out + (size_t)row * Wo;
+    for (int pw = threadIdx.x; pw < Wo; pw += 32) {
+        int tw = (pw - pad + W) % W;
+        if (flip) tw = (2 * W - 1 - tw) % W;
+        dst[pw] = __ldg(src + tw);
     }
 }
 
@@ -442,24 +455,23 @@ __global__ void sphere_pad_bwd_kernel(float* __restrict__ bottom, float* __restr
 }
 
 // sphere_cut_edge_cuda.cu:31-41 (crop) / :64-78 (zero-pad back)
-__global__ void sphere_cut_edge_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H, int W, int pad,
-                                       int backward) {
+__global__ void __launch_bounds__(32 * ROWS_PER_CTA) sphere_cut_edge_kernel(const float* __restrict__ in, float* __restrict__ out, int NC,
+                                                                          int H, int W, int pad, int backward) {
     const int Ho = H - 2 * pad, Wo = W - 2 * pad;
+    const int row = blockIdx.x * ROWS_PER_CTA + threadIdx.y;  // output row
     if (!backward) {
-        const size_t total = (size_t)NC * Ho * Wo;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const int w = (int)(i % Wo), h = (int)((i / Wo) % Ho);
-            const size_t n = i / ((size_t)Wo * Ho);
-            out[i] = in[(n * H + h + pad) * W + w + pad];
-        }
+        if (row >= NC * Ho) return;
+        const int n = row / Ho, h = row % Ho;
+        const float* src = in + ((size_t)n * H + h + pad) * W + pad;
+        float* dst = out + (size_t)row * Wo;
+        for (int w = threadIdx.x; w < Wo; w += 32) dst[w] = __ldg(src + w);
     } else {
-        const size_t total = (size_t)NC * H * W;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const int w = (int)(i % W), h = (int)((i / W) % H);
-            const size_t n = i / ((size_t)W * H);
-            const bool inside = !(w < pad || w >= Wo + pad || h < pad || h >= Ho + pad);
-            out[i] = inside ? in[(n * Ho + h - pad) * Wo + w - pad] : 0.f;
-        }
+        if (row >= NC * H) return;
+        const int n = row / H, h = row % H;
+        const bool hin = h >= pad && h < Ho + pad;
+        const float* src = in + ((size_t)n * Ho + h - pad) * Wo - pad;
+        float* dst = out + (size_t)row * W;
+        for (int w = threadIdx.x; w < W; w += 32) dst[w] = (hin && w >= pad && w < Wo + pad) ? __ldg(src + w) : 0.f;
     }
 }
 
@@ -481,18 +493,29 @@ __global__ void sphere_lat_scale_kernel(const float* __restrict__ in, const floa
 }
 
 // dtow_cuda.cu:38-75 (and the backward kernels :105-142, which are the opposite direction's forward)
-__global__ void dtow_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W, int stride,
-                            int d2w) {
+// one warp per row of the WIDTH-side tensor (C/s^2, H*s, W*s); depth side (C, H, W).  d2w: contiguous stores, the
+// loads interleave s channel rows (each contiguous); w2d: contiguous loads, s interleaved store rows.
+__global__ void __launch_bounds__(32 * ROWS_PER_CTA) dtow_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, int H,
+                                                               int W, int stride, int d2w) {
     const int p2 = stride * stride;
-    const size_t total = (size_t)N * C * H * W;
-    // iterate over the depth-side tensor (C, H, W); the width side is (C/p2, H*stride, W*stride)
     const int Co = C / p2, Ho = H * stride, Wo = W * stride;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W), h = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % C);
-        const size_t n = i / ((size_t)W * H * C);
-        const int pc = c / p2, rc = c % p2;
-        const size_t j = ((n * Co + pc) * Ho + h * stride + rc / stride) * Wo + w * stride + rc % stride;
-        if (d2w) out[j] = in[i]; else out[i] = in[j];
+    const int row = blockIdx.x * ROWS_PER_CTA + threadIdx.y;
+    if (row >= N * Co * Ho) return;
+    const int ho = row % Ho, pc = (row / Ho) % Co, n = row / (Ho * Co);
+    const int c0 = pc * p2 + (ho % stride) * stride;                // depth channel of column phase 0
+    const size_t drow = (((size_t)n * C + c0) * H + ho / stride) * W;  // + phase * H * W + wo / stride
+    const size_t wrow = (size_t)row * Wo;
+    const size_t cs = (size_t)H * W;
+    if (stride == 2) {
+        for (int wo = threadIdx.x; wo < Wo; wo += 32) {
+            const size_t dj = drow + (wo & 1) * cs + (wo >> 1);
+            if (d2w) out[wrow + wo] = __ldg(in + dj); else out[dj] = __ldg(in + wrow + wo);
+        }
+    } else {
+        for (int wo = threadIdx.x; wo < Wo; wo += 32) {
+            const size_t dj = drow + (wo % stride) * cs + wo / stride;
+            if (d2w) out[wrow + wo] = __ldg(in + dj); else out[dj] = __ldg(in + wrow + wo);
+        }
     }
 }
 
@@ -650,7 +673,9 @@ extern "C" int lic360_mask_constrain(float* w_dev, int Cout, int Cin, int ksize,
 extern "C" int lic360_sphere_pad(const float* in_dev, float* out_dev, int NC, int H, int W, int pad, void* stream) {
     const size_t total = (size_t)NC * (H + 2 * pad) * (W + 2 * pad);
     if (total == 0) return LIC360_OK;
-    sphere_pad_kernel<<<stream_grid(total, 256), 256, 0, S_(stream)>>>(in_dev, out_dev, NC, H, W, pad);
+    LIC360_CHECK_ARG((size_t)NC * (H + 2 * pad) < 2000000000u, "tensor too large");
+    const int rows = NC * (H + 2 * pad);
+    sphere_pad_kernel<<<(rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA, dim3(32, ROWS_PER_CTA), 0, S_(stream)>>>(in_dev, out_dev, NC, H, W, pad);
     LAUNCH_CHECK();
     return LIC360_OK;
 }
@@ -684,7 +709,10 @@ extern "C" int lic360_sphere_cut_edge(const float* in_dev, float* out_dev, int N
                                       void* stream) {
     LIC360_CHECK_ARG(H > 2 * pad && W > 2 * pad, "tensor smaller than its border");
     const size_t total = backward ? (size_t)NC * H * W : (size_t)NC * (H - 2 * pad) * (W - 2 * pad);
-    sphere_cut_edge_kernel<<<stream_grid(total, 256), 256, 0, S_(stream)>>>(in_dev, out_dev, NC, H, W, pad, backward);
+    if (total == 0) return LIC360_OK;
+    LIC360_CHECK_ARG((size_t)NC * H < 2000000000u, "tensor too large");
+    const int rows = backward ? NC * H : NC * (H - 2 * pad);
+    sphere_cut_edge_kernel<<<(rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA, dim3(32, ROWS_PER_CTA), 0, S_(stream)>>>(in_dev, out_dev, NC, H, W, pad, backward);
     LAUNCH_CHECK();
     return LIC360_OK;
 }
@@ -710,7 +738,9 @@ extern "C" int lic360_dtow(const float* in_dev, float* out_dev, int N, int C, in
     else { LIC360_CHECK_ARG(H % stride == 0 && W % stride == 0, "size not divisible by stride"); Cd = C * stride * stride; Hd = H / stride; Wd = W / stride; }
     const size_t total = (size_t)N * Cd * Hd * Wd;
     if (total == 0) return LIC360_OK;
-    dtow_kernel<<<stream_grid(total, 256), 256, 0, S_(stream)>>>(in_dev, out_dev, N, Cd, Hd, Wd, stride, d2w);
+    LIC360_CHECK_ARG(total / ((size_t)Wd * stride) < 2000000000u, "tensor too large");
+    const int rows = N * (Cd / (stride * stride)) * Hd * stride;
+    dtow_kernel<<<(rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA, dim3(32, ROWS_PER_CTA), 0, S_(stream)>>>(in_dev, out_dev, N, Cd, Hd, Wd, stride, d2w);
     LAUNCH_CHECK();
     return LIC360_OK;
 }

@@ -39,7 +39,10 @@ __device__ __forceinline__ float gmm_bin_value(const float* wv, const float* dv,
     float v = pt - 1 - bias + 0.5;  // (float)(pt-1) - bias in float, + 0.5 in double, rounded to float
     float ps = 0, f;
     for (int i = 0; i < ng; i++) {
-        f = 0.5 + 0.5 * erff(s2 * (v - mv[i]) / dv[i]);  // erff in float; 0.5+0.5*(.) in double -> float
+        // reference: f = 0.5 + 0.5 * erff(..) evaluated in double and rounded to float.  0.5*e is exact and a double sum
+        // of two floats rounded to float is the correctly rounded float sum (53 >= 2*24+2: innocuous double rounding), so
+        // the single-rounding fmaf gives the same bits without the FP64 pipe.
+        f = fmaf(0.5f, erff(s2 * (v - mv[i]) / dv[i]), 0.5f);
         ps = ps + wv[i] * f;                              // float, contracted to FFMA as in the reference
     }
     return static_cast<int>(total * ps + 0.5);  // float product, + 0.5 in double, truncation
