@@ -34,6 +34,15 @@ def run_smoke():
         rec = n(ops.EntDecoder(lic360, params).decode(t(mask, dev), fn))
         nbytes = os.path.getsize(fn)
     assert np.array_equal(rec, q * mask), "round trip failed"
+    # 4. the product path: fused native codec (wavefront engine: TMA-fed old-term kernel + cluster chain kernels), both streams
+    import lic360_pipeline as pl
+    q2, mask2, lv2 = synthetic_latent(8, H=16, W=32)
+    cp = pl.make_codec_params(dev, seed=5)
+    fused = pl.FusedCodec(cp, H=16, W=32)
+    bi, bc = fused.encode(t(q2, dev), t(mask2, dev), t(lv2, dev))
+    code, mup = fused.decode(bi, bc)
+    assert np.array_equal(n(code), q2 * mask2) and np.array_equal(n(mup), mask2), "fused codec round trip failed"
     torch.cuda.synchronize()
-    print("smoke OK: conv rel err %.2e, EC==DC bitwise, tables within 1 count of the oracle, round trip of %d symbols in %d bytes, %d native launches"
-          % (rel_err(ec, ref), int(mask.sum()), nbytes, lic360.launch_count() - l0))
+    print("smoke OK: conv rel err %.2e, EC==DC bitwise, tables within 1 count of the oracle, round trip of %d symbols in %d bytes, "
+          "fused codec round trip in %d+%d bytes, %d native launches"
+          % (rel_err(ec, ref), int(mask.sum()), nbytes, len(bi), len(bc), lic360.launch_count() - l0))

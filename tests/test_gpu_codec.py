@@ -152,3 +152,42 @@ def test_fused_codec_rejects_bad_input():
         fused.decode(bi, bc[: len(bc) // 2])
     except RuntimeError as e:
         assert "coder" in str(e)
+
+
+def test_fused_codec_serialized_mode_and_generic_chain(monkeypatch):
+    """The profile mode (kernels launched one by one with events, lic360_codec_set_mode(1)) and the generic chain kernel
+    (LIC360_WF_GENERIC_CHAIN: the fallback for nets that neither have 4 channels per group nor a single group) decode the
+    same bytes to the same symbols as the default pipelined path with the specialised chain kernels."""
+    import lic360_pipeline as pl
+    H, W = 12, 20
+    q, mask, lv = synthetic_latent(41, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=41)
+    tq, tm, tl = t(q, DEV), t(mask, DEV), t(lv, DEV)
+    fused = pl.FusedCodec(params, H=H, W=W)
+    bi, bc = fused.encode(tq, tm, tl)
+    code0, m0 = fused.decode(bi, bc)
+    assert np.array_equal(n(code0), q * mask) and np.array_equal(n(m0), mask)
+    fused.set_mode(1)
+    code1, m1 = fused.decode(bi, bc)
+    kt = fused.kernel_times(0)
+    assert kt['steps'] == H + W + 48 - 2 and kt['old_ms'] > 0 and kt['chain_ms'] > 0
+    assert np.array_equal(n(code1), n(code0)) and np.array_equal(n(m1), n(m0))
+    monkeypatch.setenv("LIC360_WF_GENERIC_CHAIN", "1")
+    monkeypatch.setenv("LIC360_WF_CLUSTER", "8")
+    generic = pl.FusedCodec(params, H=H, W=W)
+    assert generic.encode(tq, tm, tl) == (bi, bc)
+    code2, m2 = generic.decode(bi, bc)
+    assert np.array_equal(n(code2), n(code0)) and np.array_equal(n(m2), n(m0))
+
+
+def test_fused_codec_1024x2048_latent():
+    """LIC3602K shape (configs[2]): latent (1,48,128,256), 430 + 191 wavefront steps, two items per chain thread."""
+    import lic360_pipeline as pl
+    H, W = 128, 256
+    q, mask, lv = synthetic_latent(43, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=43)
+    fused = pl.FusedCodec(params, H=H, W=W)
+    bi, bc = fused.encode(t(q, DEV), t(mask, DEV), t(lv, DEV))
+    code, mup = fused.decode(bi, bc)
+    assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
+    assert 0 < len(bc) < q.size and 0 < len(bi) < lv.size
