@@ -17,7 +17,9 @@
 // ones behind CconvEcOp/CconvDcOp (conv.cu) and the row arithmetic is shared with EntropyGmmTableOp/EntropyTableOp
 // (tables_dev.cuh), so per-op and fused paths are interchangeable bit for bit.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <vector>
 #include "coder_internal.h"
@@ -46,6 +48,20 @@ struct NetDesc {
     int graph_nodes = 0;
     WfEngine wf;       // decoder form of the network (wavefront.cu)
     double t_kernel[5] = {0, 0, 0, 0, 0};  // profile mode: ms in old / prev / chain / scatter+rows kernels, steps
+    // per-bitstream execution context: the two streams of an image are coded concurrently
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof[6] = {nullptr};
+    int* ctr_dev = nullptr;             // current wavefront step (device counter)
+    int* done_dev = nullptr;            // CTA counter of the rows kernel
+    int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
+    uint16_t* rows_dev = nullptr;       // encode: all rows of the stream
+    uint16_t* rows_host = nullptr;      // pinned
+    uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
+    float* syms_host = nullptr;         // mapped pinned: decoded symbols of one step
+    int row_bytes = 16;                 // packed row size (16 B code stream, 128 B importance stream)
+    double t_host_coder = 0, t_gpu_wait = 0, t_done = 0;
+    lic360_coder* coder = nullptr;
+    char err[256] = {0};                // error text of a worker thread (set_error is thread-local)
 };
 
 }  // namespace lic360
@@ -54,22 +70,13 @@ using namespace lic360;
 
 struct lic360_codec {
     int device = 0, H = 0, W = 0;
-    cudaStream_t stream = nullptr, side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof[6] = {nullptr};
-    int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
-    int* done_dev = nullptr;            // CTA counter of the rows kernel
     int mode = 0;                       // 0: pipelined graph replay, 1: serialized launches with per-kernel event timing
     NetDesc code, imp;
-    int* ctr_dev = nullptr;
-    uint16_t* rows_dev = nullptr;       // encode: all rows of a stream
-    uint16_t* rows_host = nullptr;      // pinned
-    uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
-    float* syms_host = nullptr;         // mapped pinned: decoded symbols of one step
-    float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2)
-    float* mask192_dev = nullptr;
-    lic360_coder* coder[2] = {nullptr, nullptr};
+    float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2), filled diagonal by diagonal
+    float* mask192_dev = nullptr;       // scratch: Imp2mask output
+    std::atomic<int> imp_ready{0};      // decode: importance levels of diagonals < imp_ready are in levels_dev
+    std::atomic<int> abort_flag{0};     // decode: one of the two stream loops failed
     double t_host_coder = 0, t_total = 0, t_gpu_wait = 0, t_imp = 0, t_gpu_steps = 0, t_gpu_steps_imp = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace lic360 {
@@ -219,7 +226,10 @@ __device__ __forceinline__ void rows_done(int* done, volatile int* flag, int ste
 // decoder: CDF rows of the slab of step *ctr from the engine's last frame (group-major channel-last, 3 nets x G x 3).
 // 8 lanes per symbol: lane j computes bin j (the 21 erff of a row are the critical path of this latency-bound kernel),
 // lane 0 gathers the bins, runs the monotonic fix-up and stores the packed 16-byte row.
-__global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __restrict__ mask, const int32_t* __restrict__ idx,
+// The mask bit of a symbol comes straight from the decoded importance level of its 2x2 cell (Imp2mask + Dtow fused:
+// mask_up[g][h][w] = (4g + 2(h%2) + (w%2)) < 4*level[h/2][w/2], imp2mask_cuda.cu:25-38, dtow_cuda.cu:38-56), so the code
+// stream only needs the importance diagonals that are already decoded and the two streams decode concurrently.
+__global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __restrict__ levels, const int32_t* __restrict__ idx,
                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
                                    int G, int H, int W, int Dp, int Hp, float s2, int* done, int* flag) {
     const int step = *ctr;
@@ -249,8 +259,8 @@ __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __r
     for (int k = 1; k < 8; k++) o[k] = __shfl_sync(0xffffffffu, bin, (threadIdx.x & 24) + k);
     if (live && j == 0) {
         fixup_row(o, 8, true);
-        const size_t pos = ((size_t)tc * H + th) * W + tw;
-        pack_gmm_row(o, 0, mask[pos] < 0.5f ? 0 : 1, rows + (size_t)l * 8);
+        const int lvl = (int)(levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
+        pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows + (size_t)l * 8);
     }
     rows_done(done, flag, step);
 }
@@ -386,10 +396,10 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     const int tgrid = (n.max_len + 127) / 128;
     if (ev) LIC360_CUDA(cudaEventRecord(ev[0], s));
     if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.G, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
     else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, 1, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("scatter kernel");
@@ -398,10 +408,10 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
         // parallel graph branch, forked AFTER the scatter (the old terms of step p+1 read the symbols of wavefront p-1 it
         // just wrote) and joined before the counter advances.  The branch runs at the lowest priority: the block scheduler
         // stops feeding it while the chain's clusters are waiting for SMs, and it fills the SMs the chain leaves idle.
-        LIC360_CUDA(cudaEventRecord(c->ev_fork, s));
-        LIC360_CUDA(cudaStreamWaitEvent(side, c->ev_fork, 0));
+        LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
+        LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
         LIC360_CUDA(wf_launch_old(n.wf, 1, side));
-        LIC360_CUDA(cudaEventRecord(c->ev_join, side));
+        LIC360_CUDA(cudaEventRecord(n.ev_join, side));
     }
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
     LIC360_CUDA(wf_launch_prev(n.wf, s));
@@ -411,20 +421,20 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
     if (is_code)
-        gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, s>>>(n.wf.fc[12], c->mask192_dev /* = mask_up, set before the first step */, n.idx_dev,
-                                                 n.steps_dev, c->ctr_dev, c->rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
-                                                 (float)(1. / sqrt(2.0)), c->done_dev, c->flag_host);
+        gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, s>>>(n.wf.fc[12], c->levels_dev, n.idx_dev,
+                                                 n.steps_dev, n.ctr_dev, n.rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
+                                                 (float)(1. / sqrt(2.0)), n.done_dev, n.flag_host);
     else
-        imp_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_step_host, n.H, n.W, w.Dp, w.Hp,
-                                                 c->done_dev, c->flag_host);
+        imp_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
+                                                 n.done_dev, n.flag_host);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
-    if (fork) LIC360_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    if (fork) LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_join, 0));
     else LIC360_CUDA(wf_launch_old(n.wf, 1, s));
     WF_DEBUG_SYNC("old-term kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
-    advance_kernel<<<1, 1, 0, s>>>(c->ctr_dev);
+    advance_kernel<<<1, 1, 0, s>>>(n.ctr_dev);
     LAUNCH_CHECK();
     return LIC360_OK;
 }
@@ -432,12 +442,12 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
 // capture one decode step of a stream into a graph (replayed for every step)
 static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
     if (n.graph) return LIC360_OK;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = n.stream;
     cudaGraph_t g;
     const long long l0 = g_launches;
     LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     static const bool overlap = getenv("LIC360_WF_OVERLAP") != nullptr;  // measured slower on B200 (the branch delays the chain clusters): off by default
-    const int rc = launch_step(c, n, is_code, s, overlap ? c->side : s, nullptr);
+    const int rc = launch_step(c, n, is_code, s, overlap ? n.side : s, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &g);
     n.graph_nodes = (int)(g_launches - l0);
     g_launches = l0;  // captured, not launched: replays are counted in decode_stream
@@ -474,6 +484,39 @@ static double ms_since(clk::time_point t0) { return std::chrono::duration<double
 
 extern "C" {
 
+static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int prio_lo) {
+    n.row_bytes = row_bytes;
+    LIC360_CUDA(cudaStreamCreateWithPriority(&n.stream, cudaStreamNonBlocking, prio_hi));
+    LIC360_CUDA(cudaStreamCreateWithPriority(&n.side, cudaStreamNonBlocking, prio_lo));
+    LIC360_CUDA(cudaEventCreateWithFlags(&n.ev_fork, cudaEventDisableTiming));
+    LIC360_CUDA(cudaEventCreateWithFlags(&n.ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 6; i++) LIC360_CUDA(cudaEventCreate(&n.ev_prof[i]));
+    LIC360_CUDA(cudaMalloc(&n.ctr_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
+    LIC360_CUDA(cudaHostAlloc(&n.flag_host, sizeof(int), cudaHostAllocMapped));
+    n.coder = lic360_coder_create("", fill);
+    return n.coder ? LIC360_OK : LIC360_ERR_ARG;
+}
+
+static int ctx_buffers(NetDesc& n) {
+    LIC360_CUDA(cudaMalloc(&n.rows_dev, (size_t)n.total_rows * n.row_bytes));
+    LIC360_CUDA(cudaHostAlloc(&n.rows_host, (size_t)n.total_rows * n.row_bytes, cudaHostAllocDefault));
+    LIC360_CUDA(cudaHostAlloc(&n.rows_step_host, (size_t)n.max_len * n.row_bytes, cudaHostAllocMapped));
+    LIC360_CUDA(cudaHostAlloc(&n.syms_host, (size_t)n.max_len * sizeof(float), cudaHostAllocMapped));
+    return LIC360_OK;
+}
+
+static void ctx_free(NetDesc& n) {
+    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFreeHost(n.flag_host);
+    cudaFree(n.rows_dev); cudaFreeHost(n.rows_host); cudaFreeHost(n.rows_step_host); cudaFreeHost(n.syms_host);
+    if (n.ev_fork) cudaEventDestroy(n.ev_fork);
+    if (n.ev_join) cudaEventDestroy(n.ev_join);
+    for (int i = 0; i < 6; i++) if (n.ev_prof[i]) cudaEventDestroy(n.ev_prof[i]);
+    if (n.side) cudaStreamDestroy(n.side);
+    if (n.stream) cudaStreamDestroy(n.stream);
+    lic360_coder_destroy(n.coder);
+}
+
 lic360_codec* lic360_codec_create(int device, int H, int W) {
     if (H <= 0 || W <= 0 || (H % 2) || (W % 2)) { set_error("codec: latent size must be positive and even"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error("codec: cudaSetDevice(%d) failed", device); return nullptr; }
@@ -483,30 +526,15 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
     net_init(c->imp, 1, 144, 49, 1, H / 2, W / 2);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    // the critical branch of a decode step runs at the highest priority, the next step's old terms at the lowest
-    bool ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
-    ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 6; i++) ok = ok && cudaEventCreate(&c->ev_prof[i]) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->ctr_dev, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->done_dev, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&c->flag_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    bool ok = ctx_alloc(c->code, 16, 3.5f, prio_hi, prio_lo) == LIC360_OK && ctx_alloc(c->imp, 128, 3.5f, prio_hi, prio_lo) == LIC360_OK;
     ok = ok && net_alloc(c->code) == LIC360_OK && net_alloc(c->imp) == LIC360_OK;
-    ok = ok && wf_init(c->code.wf, 48, 4, 3, 3, H, W, c->code.idx_dev, c->code.steps_dev, c->ctr_dev, c->code.nsteps, c->code.max_len) == LIC360_OK;
-    ok = ok && wf_init(c->imp.wf, 1, 144, 49, 1, H / 2, W / 2, c->imp.idx_dev, c->imp.steps_dev, c->ctr_dev, c->imp.nsteps, c->imp.max_len) == LIC360_OK;
-    const bool wf_ok = ok;
-    const size_t rows_bytes = std::max((size_t)c->code.total_rows * 16, (size_t)c->imp.total_rows * 128);
-    const size_t step_bytes = std::max((size_t)c->code.max_len * 16, (size_t)c->imp.max_len * 128);
-    ok = ok && cudaMalloc(&c->rows_dev, rows_bytes) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&c->rows_host, rows_bytes, cudaHostAllocDefault) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&c->rows_step_host, step_bytes, cudaHostAllocMapped) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&c->syms_host, std::max(c->code.max_len, c->imp.max_len) * sizeof(float), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && ctx_buffers(c->code) == LIC360_OK && ctx_buffers(c->imp) == LIC360_OK;
+    const bool pre_ok = ok;
+    ok = ok && wf_init(c->code.wf, 48, 4, 3, 3, H, W, c->code.idx_dev, c->code.steps_dev, c->code.ctr_dev, c->code.nsteps, c->code.max_len) == LIC360_OK;
+    ok = ok && wf_init(c->imp.wf, 1, 144, 49, 1, H / 2, W / 2, c->imp.idx_dev, c->imp.steps_dev, c->imp.ctr_dev, c->imp.nsteps, c->imp.max_len) == LIC360_OK;
+    const bool wf_ok = ok || !pre_ok;
     ok = ok && cudaMalloc(&c->levels_dev, (size_t)(H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mask192_dev, (size_t)192 * (H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
-    c->coder[0] = lic360_coder_create("", 3.5f);
-    c->coder[1] = lic360_coder_create("", 3.5f);
     if (!ok) {
         if (wf_ok) set_error("codec: allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));  // else: wf_init's message
         lic360_codec_destroy(c);
@@ -520,17 +548,8 @@ void lic360_codec_destroy(lic360_codec* c) {
     cudaSetDevice(c->device);
     net_free(c->code); net_free(c->imp);
     wf_free(c->code.wf); wf_free(c->imp.wf);
-    cudaFree(c->done_dev); cudaFreeHost(c->flag_host);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    for (int i = 0; i < 6; i++) if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
-    if (c->side) cudaStreamDestroy(c->side);
-    cudaFree(c->ctr_dev); cudaFree(c->rows_dev); cudaFreeHost(c->rows_host); cudaFreeHost(c->rows_step_host);
-    cudaFreeHost(c->syms_host); cudaFree(c->levels_dev); cudaFree(c->mask192_dev);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    lic360_coder_destroy(c->coder[0]); lic360_coder_destroy(c->coder[1]);
+    ctx_free(c->code); ctx_free(c->imp);
+    cudaFree(c->levels_dev); cudaFree(c->mask192_dev);
     delete c;
 }
 
@@ -549,11 +568,11 @@ int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const floa
         LIC360_CUDA(cudaMalloc(&n.bias[layer], nb * sizeof(float)));
         LIC360_CUDA(cudaMalloc(&n.slope[layer], nb * sizeof(float)));
     }
-    int rc = lic360_cconv_pack(w_dev, n.wp[layer], n.wq[layer], n.nsets, n.Cin[layer], n.Cout[layer], n.G, 5, n.constrain[layer], c->stream);
+    int rc = lic360_cconv_pack(w_dev, n.wp[layer], n.wq[layer], n.nsets, n.Cin[layer], n.Cout[layer], n.G, 5, n.constrain[layer], n.stream);
     if (rc) return rc;
-    LIC360_CUDA(cudaMemcpyAsync(n.bias[layer], bias_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    if (slope_dev) LIC360_CUDA(cudaMemcpyAsync(n.slope[layer], slope_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    LIC360_CUDA(cudaStreamSynchronize(c->stream));
+    LIC360_CUDA(cudaMemcpyAsync(n.bias[layer], bias_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, n.stream));
+    if (slope_dev) LIC360_CUDA(cudaMemcpyAsync(n.slope[layer], slope_dev, nb * sizeof(float), cudaMemcpyDeviceToDevice, n.stream));
+    LIC360_CUDA(cudaStreamSynchronize(n.stream));
     wf_set_layer(n.wf, layer, n.wp[layer], n.wq[layer], n.bias[layer], n.act[layer] ? n.slope[layer] : nullptr);
     if (n.graph) { cudaGraphExecDestroy(n.graph); n.graph = nullptr; }  // the graph holds the kernel parameters by value
     n.set[layer] = true;
@@ -568,33 +587,26 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
     if (rc) return rc;
     const auto t0 = clk::now();
     c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_imp = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0;
-    cudaStream_t s = c->stream;
-    // ---- importance stream (lic360_demo.py:173-189): Scale(-1, 2/47) -> net -> rows of all 2048 symbols
+    // The two bitstreams are independent: both networks are enqueued on their own CUDA streams first, then the host
+    // codes the (small) importance stream while the code-stream network is still running.
+    // ---- importance stream (lic360_demo.py:173-189): Scale(-1, 2/47) -> net -> rows of all symbols
     {
         NetDesc& n = c->imp;
+        cudaStream_t s = n.stream;
         const int HW = n.H * n.W;
         rc = lic360_scale(imp_dev, n.frame[0], HW, -1.0f, (float)(2. / (48 - 1.)), s);
         if (rc) return rc;
         rc = run_ec_net(n, s);
         if (rc) return rc;
-        imp_rows_kernel<<<(HW + 127) / 128, 128, 0, s>>>(n.frame[12], imp_dev, n.idx_dev, n.steps_dev, c->ctr_dev, c->rows_dev, n.H, n.W, 1);
+        imp_rows_kernel<<<(HW + 127) / 128, 128, 0, s>>>(n.frame[12], imp_dev, n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_dev, n.H, n.W, 1);
         LAUNCH_CHECK();
-        LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 128, cudaMemcpyDeviceToHost, s));
-        auto tw = clk::now();
+        LIC360_CUDA(cudaMemcpyAsync(n.rows_host, n.rows_dev, (size_t)n.total_rows * 128, cudaMemcpyDeviceToHost, s));
         c->t_gpu_steps_imp = ms_since(t0);  // host time spent enqueueing the importance-stream work
-        LIC360_CUDA(cudaStreamSynchronize(s));
-        c->t_gpu_wait += ms_since(tw);
-        c->t_imp = ms_since(t0);
-        auto th = clk::now();
-        lic360_coder_start_encoder_mem(c->coder[1]);
-        rc = coder_encode_packed_imp(c->coder[1], c->rows_host, n.total_rows);
-        if (rc) return rc;
-        if (lic360_coder_finish_mem(c->coder[1]) < 0) return LIC360_ERR_CODER;
-        c->t_host_coder += ms_since(th);
     }
     // ---- code stream (lic360_demo.py:124-141)
     {
         NetDesc& n = c->code;
+        cudaStream_t s = n.stream;
         const auto tq0 = clk::now();
         const int nel = n.G * n.H * n.W;
         prep_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(code_dev, mask_dev, n.frame[0], nel, 3.5f);
@@ -602,18 +614,34 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
         rc = run_ec_net(n, s);
         if (rc) return rc;
         gmm_rows_kernel<<<(nel + 127) / 128, 128, 0, s>>>(n.frame[12], code_dev, mask_dev, n.idx_dev, n.steps_dev, n.row_off_dev,
-                                                          c->ctr_dev, c->rows_dev, n.G, n.H, n.W, 1, (float)(1. / sqrt(2.0)));
+                                                          n.ctr_dev, n.rows_dev, n.G, n.H, n.W, 1, (float)(1. / sqrt(2.0)));
         LAUNCH_CHECK();
-        LIC360_CUDA(cudaMemcpyAsync(c->rows_host, c->rows_dev, (size_t)n.total_rows * 16, cudaMemcpyDeviceToHost, s));
+        LIC360_CUDA(cudaMemcpyAsync(n.rows_host, n.rows_dev, (size_t)n.total_rows * 16, cudaMemcpyDeviceToHost, s));
         c->t_gpu_steps = ms_since(tq0);  // host time spent enqueueing the code-stream work
+    }
+    {
+        NetDesc& n = c->imp;
         auto tw = clk::now();
-        LIC360_CUDA(cudaStreamSynchronize(s));
+        LIC360_CUDA(cudaStreamSynchronize(n.stream));
         c->t_gpu_wait += ms_since(tw);
         auto th = clk::now();
-        lic360_coder_start_encoder_mem(c->coder[0]);
-        rc = coder_encode_packed_gmm(c->coder[0], c->rows_host, n.total_rows);
+        lic360_coder_start_encoder_mem(n.coder);
+        rc = coder_encode_packed_imp(n.coder, n.rows_host, n.total_rows);
         if (rc) return rc;
-        if (lic360_coder_finish_mem(c->coder[0]) < 0) return LIC360_ERR_CODER;
+        if (lic360_coder_finish_mem(n.coder) < 0) return LIC360_ERR_CODER;
+        c->t_host_coder += ms_since(th);
+        c->t_imp = ms_since(t0);
+    }
+    {
+        NetDesc& n = c->code;
+        auto tw = clk::now();
+        LIC360_CUDA(cudaStreamSynchronize(n.stream));
+        c->t_gpu_wait += ms_since(tw);
+        auto th = clk::now();
+        lic360_coder_start_encoder_mem(n.coder);
+        rc = coder_encode_packed_gmm(n.coder, n.rows_host, n.total_rows);
+        if (rc) return rc;
+        if (lic360_coder_finish_mem(n.coder) < 0) return LIC360_ERR_CODER;
         c->t_host_coder += ms_since(th);
     }
     c->t_total = ms_since(t0);
@@ -622,21 +650,22 @@ int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mas
 
 long lic360_codec_stream_size(lic360_codec* c, int stream_id) {
     long n = 0;
-    coder_bytes(c->coder[stream_id ? 1 : 0], &n);
+    coder_bytes(stream_id ? c->imp.coder : c->code.coder, &n);
     return n;
 }
 
 long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long cap) {
-    return lic360_coder_get_bytes(c->coder[stream_id ? 1 : 0], out, cap);
+    return lic360_coder_get_bytes(stream_id ? c->imp.coder : c->code.coder, out, cap);
 }
 
-// wait for the rows of step p without synchronising the stream (the side branch of the graph may still be running)
-static int wait_rows(lic360_codec* c, int p) {
-    volatile int* f = c->flag_host;
+// wait for the rows of step p without synchronising the stream (a later kernel of the step graph may still be running)
+static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
+    volatile int* f = n.flag_host;
     const auto t0 = clk::now();
     for (unsigned spins = 1; *f != p + 1; spins++) {
         if ((spins & 0x3FFF) == 0) {
-            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (c->abort_flag.load()) { set_error("codec: aborted (the other stream failed)"); return LIC360_ERR_CUDA; }
+            const cudaError_t e = cudaStreamQuery(n.stream);
             if (e == cudaSuccess) {
                 if (*f == p + 1) break;
                 set_error("codec: step %d finished without producing its rows", p);
@@ -652,50 +681,77 @@ static int wait_rows(lic360_codec* c, int p) {
     return LIC360_OK;
 }
 
-static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code, lic360_coder* coder) {
-    cudaStream_t s = c->stream;
-    int rc = c->mode == 0 ? build_step_graph(c, n, is_code) : LIC360_OK;
-    if (rc) return rc;
-    *c->flag_host = 0;
+static int final_scatter(lic360_codec* c, NetDesc& n, bool is_code) {
+    // scatter the symbols of the last step (the final TileInput of lic360_demo.py:236,285)
+    const WfNetDev& w = n.wf.dev;
+    const int tgrid = (n.max_len + 127) / 128;
+    cudaStream_t s = n.stream;
+    if (is_code)
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.G, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
+    else
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, 1, n.H, n.W,
+                                                  w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
+    LAUNCH_CHECK();
+    return LIC360_OK;
+}
+
+// The wavefront loop of one bitstream.  is_code: before step p the importance levels of every 2x2 cell the slab touches
+// must be decoded (cells on importance diagonals <= min(p, H+W-2)/2): the loop waits on c->imp_ready, which the
+// importance loop (running concurrently on another host thread and CUDA stream) publishes.
+static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
+    cudaStream_t s = n.stream;
+    int rc = LIC360_OK;
+    *n.flag_host = 0;
+    n.t_host_coder = 0; n.t_gpu_wait = 0;
     LIC360_CUDA(wf_clear(n.wf, s));
-    LIC360_CUDA(cudaMemsetAsync(c->ctr_dev, 0, sizeof(int), s));
-    LIC360_CUDA(cudaMemsetAsync(c->done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.done_dev, 0, sizeof(int), s));
     LIC360_CUDA(wf_launch_old(n.wf, 0, s));  // old terms of step 0 (all zero, but it keeps the schedule uniform)
     if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
     for (int p = 0; p < n.nsteps; p++) {
         auto tw = clk::now();
+        if (is_code) {
+            const int need = std::min(p, n.H + n.W - 2) / 2 + 1;
+            for (unsigned spins = 1; c->imp_ready.load(std::memory_order_acquire) < need; spins++) {
+                if ((spins & 0xFFF) == 0 && (c->abort_flag.load() || ms_since(tw) > 20000.)) {
+                    set_error("codec: the importance stream did not deliver the levels the code stream needs");
+                    return LIC360_ERR_CODER;
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+        }
         if (c->mode == 0) {
             LIC360_CUDA(cudaGraphLaunch(n.graph, s));
             g_launches += n.graph_nodes;
-            rc = wait_rows(c, p);
+            rc = wait_rows(c, n, p);
             if (rc) return rc;
         } else {
-            rc = launch_step(c, n, is_code, s, s, c->ev_prof);
+            rc = launch_step(c, n, is_code, s, s, n.ev_prof);
             if (rc) return rc;
             LIC360_CUDA(cudaStreamSynchronize(s));
             float ms[5];
-            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], c->ev_prof[i], c->ev_prof[i + 1]);
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], n.ev_prof[i], n.ev_prof[i + 1]);
             n.t_kernel[0] += ms[4]; n.t_kernel[1] += ms[1]; n.t_kernel[2] += ms[2]; n.t_kernel[3] += ms[0] + ms[3]; n.t_kernel[4] += 1;
         }
-        c->t_gpu_wait += ms_since(tw);
+        n.t_gpu_wait += ms_since(tw);
+        if (!is_code) c->imp_ready.store(p, std::memory_order_release);  // the scatter of this step wrote diagonal p-1
         auto th = clk::now();
         const int len = n.steps[p].len;
-        rc = is_code ? coder_decode_packed_gmm(coder, c->rows_step_host, len, c->syms_host)
-                     : coder_decode_packed_imp(coder, c->rows_step_host, len, c->syms_host);
-        c->t_host_coder += ms_since(th);
+        rc = is_code ? coder_decode_packed_gmm(n.coder, n.rows_step_host, len, n.syms_host)
+                     : coder_decode_packed_imp(n.coder, n.rows_step_host, len, n.syms_host);
+        n.t_host_coder += ms_since(th);
         if (rc) return rc;
     }
-    // scatter the symbols of the last step (the final TileInput of lic360_demo.py:236,285)
-    const WfNetDev& w = n.wf.dev;
-    const int tgrid = (n.max_len + 127) / 128;
-    if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, n.G, n.H, n.W,
-                                                  w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
-    else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(c->syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, c->ctr_dev, 1, n.H, n.W,
-                                                  w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
-    LAUNCH_CHECK();
+    rc = final_scatter(c, n, is_code);
+    if (rc) return rc;
+    if (!is_code) {
+        LIC360_CUDA(cudaStreamSynchronize(s));
+        c->imp_ready.store(n.nsteps + 1, std::memory_order_release);  // every diagonal is in levels_dev
+    }
     return LIC360_OK;
 }
 
@@ -707,31 +763,53 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     if (rc == LIC360_OK) rc = check_params(c->imp);
     if (rc) return rc;
     const auto t0 = clk::now();
-    c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0;
-    cudaStream_t s = c->stream;
-    // ---- importance stream (lic360_demo.py:272-290) -> levels -> Imp2mask(48,192) -> Dtow -> mask_up
-    lic360_coder_start_decoder_mem(c->coder[1], imp_bytes, n_imp);
-    rc = decode_stream(c, c->imp, false, c->coder[1]);
-    if (rc) return rc;
-    c->t_imp = ms_since(t0);
+    c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0; c->t_imp = 0;
+    c->imp_ready.store(0);
+    c->abort_flag.store(0);
+    if (c->mode == 0) {  // both step graphs exist before the second host thread starts
+        rc = build_step_graph(c, c->imp, false);
+        if (rc == LIC360_OK) rc = build_step_graph(c, c->code, true);
+        if (rc) return rc;
+    }
+    lic360_coder_start_decoder_mem(c->imp.coder, imp_bytes, n_imp);
+    lic360_coder_start_decoder_mem(c->code.coder, code_bytes, n_code);
+    // ---- importance stream (lic360_demo.py:272-290) and code stream (:220-238), concurrently in the pipelined mode: the
+    // code stream only reads importance levels that are already decoded (decode_stream).  Serialized in profile mode.
+    int rc_imp = LIC360_OK;
+    c->imp.err[0] = 0;
+    auto imp_loop = [&]() {
+        cudaSetDevice(c->device);
+        rc_imp = decode_stream(c, c->imp, false);
+        if (rc_imp) {
+            snprintf(c->imp.err, sizeof(c->imp.err), "%s", lic360_last_error());
+            c->abort_flag.store(1);
+        }
+        c->t_imp = ms_since(t0);
+    };
+    if (c->mode == 0) {
+        std::thread worker(imp_loop);
+        rc = decode_stream(c, c->code, true);
+        if (rc) c->abort_flag.store(1);
+        worker.join();
+    } else {
+        imp_loop();
+        if (rc_imp == LIC360_OK) rc = decode_stream(c, c->code, true);
+    }
+    if (rc_imp) { set_error("%s", c->imp.err); cudaStreamSynchronize(c->code.stream); cudaStreamSynchronize(c->imp.stream); return rc_imp; }
+    if (rc) { cudaStreamSynchronize(c->code.stream); cudaStreamSynchronize(c->imp.stream); return rc; }
+    // ---- outputs: mask_up = Dtow(Imp2mask(levels)) (lic360_demo.py:285-290), code = frame + 3.5 * mask (:236-237)
+    cudaStream_t s = c->code.stream;
     rc = lic360_imp2mask(c->levels_dev, c->mask192_dev, 1, 192, c->imp.H, c->imp.W, 48, s);
     if (rc) return rc;
     rc = lic360_dtow(c->mask192_dev, mask_out_dev, 1, 192, c->imp.H, c->imp.W, 2, 1, s);
     if (rc) return rc;
-    // the code-stream graph reads the mask through mask192_dev's slot: point it at the caller's mask_up instead
-    // ---- code stream (lic360_demo.py:220-238)
-    lic360_coder_start_decoder_mem(c->coder[0], code_bytes, n_code);
-    {
-        // mask_up must live in codec-owned memory because the graph captured its address: reuse frame-sized scratch
-        LIC360_CUDA(cudaMemcpyAsync(c->mask192_dev, mask_out_dev, (size_t)48 * c->H * c->W * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    }
-    rc = decode_stream(c, c->code, true, c->coder[0]);
-    if (rc) return rc;
     const int nel = 48 * c->H * c->W;
-    finish_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(c->code.wf.fc[0], c->mask192_dev, code_out_dev, 48, c->H, c->W,
+    finish_code_kernel<<<stream_grid(nel, 256), 256, 0, s>>>(c->code.wf.fc[0], mask_out_dev, code_out_dev, 48, c->H, c->W,
                                                              c->code.wf.dev.Dp, c->code.wf.dev.Hp, 3.5f);
     LAUNCH_CHECK();
     LIC360_CUDA(cudaStreamSynchronize(s));
+    c->t_host_coder = c->code.t_host_coder + c->imp.t_host_coder;
+    c->t_gpu_wait = c->code.t_gpu_wait;
     c->t_total = ms_since(t0);
     return LIC360_OK;
 }
