@@ -28,8 +28,12 @@ namespace lic360 {
 // instruction" on sm_100, tools/tma_probe.cu), so the box starts at (hbase - 2) rounded down to 4 and is 40 wide.
 constexpr int WF_BOX_W = 40;
 constexpr int WF_BAND = 9 * WF_BOX_W;                 // cells per channel
-constexpr int WF_BAND_BYTES = DC_STAGE * WF_BAND * 4;  // 5760
-constexpr int WF_STAGE_BYTES = 7424;                  // band + 4 x 25 float4 weights (1600 B), padded to a multiple of 128
+#ifndef WF_STAGE_CH
+#define WF_STAGE_CH 4
+#endif
+constexpr int WF_STAGE = WF_STAGE_CH;                 // input channels per TMA stage
+constexpr int WF_BAND_BYTES = WF_STAGE * WF_BAND * 4;  // 5760 for 4 channels
+constexpr int WF_STAGE_BYTES = ((WF_BAND_BYTES + WF_STAGE * TAPS * 16 + 127) / 128) * 128;  // band + weights, multiple of 128
 
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + L.nblk * 32);      // [WF_OLD_WARPS]
     const int lane = threadIdx.x, seg = threadIdx.y;
     float* band = reinterpret_cast<float*>(base + (size_t)seg * WF_STAGE_BYTES);
-    float4* wsm = reinterpret_cast<float4*>(band + DC_STAGE * WF_BAND);
+    float4* wsm = reinterpret_cast<float4*>(band + WF_STAGE * WF_BAND);
     const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
     const unsigned wsm_s = band_s + WF_BAND_BYTES;
     const int h0 = (t.hbase - 2) & ~3;   // aligned box start (also for negative values: two's complement floor)
@@ -124,8 +128,8 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
         const int cb = min(CB, Cin - j * CB);
         const float4* wp4 = reinterpret_cast<const float4*>(L.wp) + (((size_t)t.n * L.nchunk + chunk) * Cin + j * CB) * TAPS;
-        for (int c0 = 0; c0 < cb && j * CB + c0 < lim; c0 += DC_STAGE) {
-            const int nc = min(DC_STAGE, cb - c0);
+        for (int c0 = 0; c0 < cb && j * CB + c0 < lim; c0 += WF_STAGE) {
+            const int nc = min(WF_STAGE, cb - c0);
             __syncwarp();  // every lane is done with the previous stage
             if (lane == 0) {
                 mbar_expect_tx(bar, WF_BAND_BYTES + nc * TAPS * 16);
@@ -171,9 +175,9 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
     const int cend = min((jq + 1) * CB, cin_g);
     const float4* w = reinterpret_cast<const float4*>(L.wq) +
                       ((size_t)(cls * net.nsets + n) * L.nchunk + tc * L.cpg4 + kc) * TAPS * cin_g;
-    // cell (d-4+kh+kw, group gq, h-2+kh) of the padded frame = xb + (((kh+kw) * G + gq) * Hp + kh) * cin_g
-    const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.G * net.Hp + h) * cin_g;
-    const int Hp = net.Hp, G = net.G;
+    // cell (d-4+kh+kw, group gq, h-2+kh) of the padded frame = xb + (((kh+kw) * GP + gq) * Hp + kh) * cin_g
+    const int Hp = net.Hp, G = net.G, GP = net.G + 2 * WF_GPAD;
+    const float* xb = L.xc + ((((size_t)n * net.Dp + d) * GP + WF_GPAD) * Hp + h) * cin_g;
     (void)C;
     if ((cin_g & 3) == 0 && net.G == 1) {
         // one group: input group 0 is selected by exactly the taps with kh + kw == gsel0 (3 or 4)
@@ -184,7 +188,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                 const int kw = gsel0 - kh;
                 const bool ok = kw >= 0 && kw < 5;
                 xv[kh] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) xv[kh] = wf_ldx4<CG>(xb + ((size_t)gsel0 * Hp + kh) * cin_g + c0);
+                if (ok) xv[kh] = wf_ldx4<CG>(xb + ((size_t)gsel0 * GP * Hp + kh) * cin_g + c0);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     wv[kh][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,7 +220,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                     const int gq = gsel0 - kh - kw;
                     const bool ok = gq >= 0 && gq < net.G;
                     xv[kw] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) xv[kw] = wf_ldx4<CG>(xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0);
+                    if (ok) xv[kw] = wf_ldx4<CG>(xb + (((size_t)(kh + kw) * GP + gq) * Hp + kh) * cin_g + c0);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         wv[kw][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,7 +251,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                 for (int kw = 0; kw < 5; kw++) {
                     const int gq = gsel0 - kh - kw;
                     if (gq < 0 || gq >= net.G) continue;
-                    const float* xp = xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0;
+                    const float* xp = xb + (((size_t)(kh + kw) * GP + gq) * Hp + kh) * cin_g + c0;
                     const float4* wt = w + (kh * 5 + kw) * cin_g + c0;
                     for (int c = 0; c < nc; c++) {
                         const float xx = CG ? __ldcg(xp + c) : __ldg(xp + c);
@@ -293,7 +297,8 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
     if (jq < L.nqb && valid) {
         const int cend = min((jq + 1) * CB, cin_g);
-        const float* xb = L.xc + (((size_t)t.n * net.Dp + t.d) * G * Hp + h) * cin_g;
+        const int GP = G + 2 * WF_GPAD;
+        const float* xb = L.xc + ((((size_t)t.n * net.Dp + t.d) * GP + WF_GPAD) * Hp + h) * cin_g;
         if ((cin_g & 3) == 0 && G == 1) {
             // one group: exactly the taps with kh + kw == gsel0 (== 3) contribute; all chunks of the block in flight
             float4 xv[4][5];
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
                 for (int kh = 0; kh < 5; kh++) {
                     const int kw = gsel0 - kh, c0 = jq * CB + 4 * q;
                     xv[q][kh] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (kw >= 0 && kw < 5 && c0 < cend) xv[q][kh] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gsel0 * Hp + kh) * cin_g + c0));
+                    if (kw >= 0 && kw < 5 && c0 < cend) xv[q][kh] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gsel0 * GP * Hp + kh) * cin_g + c0));
                 }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
                         const int gq = gsel0 - kh - kw;
                         xv[kh * 5 + kw] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (gq >= 0 && gq < G)
-                            xv[kh * 5 + kw] = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0));
+                            xv[kh * 5 + kw] = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)(kh + kw) * GP + gq) * Hp + kh) * cin_g + c0));
                     }
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++)
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
                     for (int kw = 0; kw < 5; kw++) {
                         const int gq = gsel0 - kh - kw;
                         if (gq < 0 || gq >= G) continue;
-                        const float* xp = xb + (((size_t)(kh + kw) * G + gq) * Hp + kh) * cin_g + c0;
+                        const float* xp = xb + (((size_t)(kh + kw) * GP + gq) * Hp + kh) * cin_g + c0;
                         const float4* wt = wf_psm + (kh * 5 + kw) * cin_g + c0;
                         for (int c = 0; c < nc; c++) {
                             const float xx = __ldg(xp + c);
@@ -548,24 +553,21 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
             }
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             if (L.has_q) {
-                const float* xb = L.xc + (((size_t)n * net.Dp + d) * net.G * net.Hp + h) * 4;
+                // tap (kh, kw), s = kh + kw, selects group tc + 4 - s: cell = xr + s * srow + kh, float4 units.  Groups outside
+                // [0, G) fall into the zero padding of the group axis (and carry zero weights): no tests, no branches.
+                const int GP = net.G + 2 * WF_GPAD;
+                const float4* xr = reinterpret_cast<const float4*>(L.xc) + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 4) * net.Hp + h;
+                const size_t srow = (size_t)(GP - 1) * net.Hp;
                 const float4* wr = wl + (size_t)(tc - tc_lo) * WF_ROW_F4;
                 float4 xv[TAPS];
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++)
 #pragma unroll
-                    for (int kw = 0; kw < 5; kw++) {
-                        const int gq = tc + 4 - kh - kw;
-                        xv[kh * 5 + kw] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (gq >= 0 && gq < net.G)
-                            xv[kh * 5 + kw] = __ldcg(reinterpret_cast<const float4*>(xb + (((size_t)(kh + kw) * net.G + gq) * net.Hp + kh) * 4));
-                    }
+                    for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = __ldcg(xr + (kh + kw) * srow + kh);
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++)
 #pragma unroll
                     for (int kw = 0; kw < 5; kw++) {
-                        const int gq = tc + 4 - kh - kw;
-                        if (gq < 0 || gq >= net.G) continue;
                         const float4 x4 = xv[kh * 5 + kw];
                         const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -798,7 +800,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     }
     if (e.nblk_max > 32 || e.nqb_max > 32) { set_error("wavefront engine: too many channels"); return LIC360_ERR_ARG; }
     for (int i = 0; i <= WF_LAYERS; i++) {
-        e.fc_floats[i] = (size_t)nsets * n.Dp * n.Hp * e.C[i];
+        e.fc_floats[i] = (size_t)nsets * n.Dp * (G + 2 * WF_GPAD) * n.Hp * (e.C[i] / G);
         LIC360_CUDA(cudaMalloc(&e.fc[i], e.fc_floats[i] * sizeof(float)));
         if (i < WF_LAYERS) {
             e.fp_floats[i] = (size_t)nsets * e.C[i] * n.D * n.HS;
@@ -823,7 +825,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     for (int l = 0; l < WF_LAYERS; l++) {
         const cuuint64_t dims[3] = {(cuuint64_t)n.HS, (cuuint64_t)n.D, (cuuint64_t)nsets * e.C[l]};
         const cuuint64_t strides[2] = {(cuuint64_t)n.HS * 4, (cuuint64_t)n.D * n.HS * 4};
-        const cuuint32_t box[3] = {WF_BOX_W, 9, 4};
+        const cuuint32_t box[3] = {WF_BOX_W, 9, WF_STAGE};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&e.maps.tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e.fp[l], dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -5,7 +5,7 @@
 //   FP  "planar skewed"   [set*C + c][D][HS]          d = h + w, HS = H rounded up to 4.  Source of the TMA box loads
 //                                                      of the old-term kernel (a 5x5 window of 32 diagonal neighbours
 //                                                      is the rectangle 36 x 9 in (h, d) coordinates).
-//   FC  "group-major channel-last"  [set][D + 8][G][H + 4][C/G]   zero border of 4 diagonals / 2 rows: the previous- and
+//   FC  "group-major channel-last"  [set][D + 8][G + 10][H + 4][C/G]   zero border of 4 diagonals / 5 groups / 2 rows: the previous- and
 //                                                      same-wavefront terms read one float4 (4 channels of a group)
 //                                                      per tap with no bounds checks, and the 32 lanes of a warp
 //                                                      (consecutive h on one diagonal, one group) read 512 contiguous bytes.
@@ -70,9 +70,11 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s);       // P
 cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s);              // P + R of step *ctr, all layers
 cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s);             // the 12-layer chain of step *ctr
 
-// first channel of group g at (d, h); cpg = channels per group of that frame
+// first channel of group g at (d, h); cpg = channels per group of that frame.  The group axis carries WF_GPAD zero
+// groups on each side: a tap of the R / Q terms may select group -5 .. G+3, which then reads zeros instead of needing a test.
+constexpr int WF_GPAD = 5;
 __host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int G, int cpg, int n, int d, int g, int h) {
-    return ((((size_t)n * Dp + d + 4) * G + g) * Hp + h + 2) * cpg;
+    return ((((size_t)n * Dp + d + 4) * (G + 2 * WF_GPAD) + g + WF_GPAD) * Hp + h + 2) * cpg;
 }
 __host__ __device__ inline size_t wf_fp_index(int D, int HS, int C, int n, int c, int d, int h) {
     return (((size_t)n * C + c) * D + d) * HS + h;

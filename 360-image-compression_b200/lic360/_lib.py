@@ -5,7 +5,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "liblic360_b200.so")
+LIB_PATH = os.environ.get("LIC360_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "liblic360_b200.so")  # override: A/B builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
