@@ -28,6 +28,32 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // band cell of position `lane`, tap (kh,kw): band[ch*DC_BAND + (lane+kh)*RS + (kh+kw)*CS]
 //   NCHW kernel  : rows = image rows, 9 columns         -> RS = 9, CS = 1,  CHS = 324
 //   skewed kernel: rows = diagonals (kh+kw), 40 columns -> RS = 1, CS = 40, CHS = 360 (TMA box, wavefront.cu)
+// u += x * w for the 4 output channels of a chunk.  With LIC360_FFMA2 the four fp32 FMAs are issued as two packed
+// fma.rn.f32x2 (sm_100: two IEEE fp32 FMAs per instruction, bit-identical results, half the FMA issue slots).
+__device__ __forceinline__ void fma4(float4& u, float xx, const float4& w4) {
+#ifdef LIC360_FFMA2
+    asm("{\n"
+        ".reg .b64 xa, wa, wb, ua, ub;\n"
+        "mov.b64 xa, {%4, %4};\n"
+        "mov.b64 wa, {%5, %6};\n"
+        "mov.b64 wb, {%7, %8};\n"
+        "mov.b64 ua, {%0, %1};\n"
+        "mov.b64 ub, {%2, %3};\n"
+        "fma.rn.f32x2 ua, xa, wa, ua;\n"
+        "fma.rn.f32x2 ub, xa, wb, ub;\n"
+        "mov.b64 {%0, %1}, ua;\n"
+        "mov.b64 {%2, %3}, ub;\n"
+        "}\n"
+        : "+f"(u.x), "+f"(u.y), "+f"(u.z), "+f"(u.w)
+        : "f"(xx), "f"(w4.x), "f"(w4.y), "f"(w4.z), "f"(w4.w));
+#else
+    u.x = fmaf(xx, w4.x, u.x);
+    u.y = fmaf(xx, w4.y, u.y);
+    u.z = fmaf(xx, w4.z, u.z);
+    u.w = fmaf(xx, w4.w, u.w);
+#endif
+}
+
 // taps with kh + kw < NS, fully unrolled with compile-time tap predicates (no per-tap compare/branch at run time)
 template <int RS, int CS, int NS>
 __device__ __forceinline__ void dc_taps_fma(const float* bw, const float4* wrow, float4& u) {
@@ -38,10 +64,7 @@ __device__ __forceinline__ void dc_taps_fma(const float* bw, const float4* wrow,
             if (kh + kw >= NS) continue;
             const float xx = bw[kh * RS + (kh + kw) * CS];
             const float4 w4 = wrow[kh * 5 + kw];
-            u.x = fmaf(xx, w4.x, u.x);
-            u.y = fmaf(xx, w4.y, u.y);
-            u.z = fmaf(xx, w4.z, u.z);
-            u.w = fmaf(xx, w4.w, u.w);
+            fma4(u, xx, w4);
         }
     }
 }

@@ -123,7 +123,16 @@ def cpu_arm(steps, warmup, sample_hw=(16, 32)):
                       % (8 * h, 8 * w, h, w, h // 2, w // 2, "reference" if O.have_ref_coder() else "restated", t)}, t
 
 
+def emit(line, real_stdout):
+    """the ONE JSON line of the contract, on the real stdout (everything else -- NCCL banners included -- goes to stderr)"""
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # keep stdout clean: libraries (NCCL prints its version banner to stdout) write to fd 1, which now points at stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -149,7 +158,7 @@ def main():
                 "config": {"workload": "configs[1]: 512x1024 ERP entropy encode+decode, batch 1 -- bounded CPU sample: " + cb["sample"]},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line, real_stdout)
         return
 
     import numpy as np
@@ -325,7 +334,7 @@ def main():
                                           "note": "oracle/_ref/lic360_ref*.so driven by the per-op loops of lic360_demo.py; reported, not the target"}
         except Exception as e:
             line["reference_cuda_ext"] = {"unavailable": repr(e)}
-    print(json.dumps(line))
+    emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 
