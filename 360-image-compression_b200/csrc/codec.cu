@@ -403,16 +403,7 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("scatter kernel");
-    const bool fork = side != s;
-    if (fork) {
-        // parallel graph branch, forked AFTER the scatter (the old terms of step p+1 read the symbols of wavefront p-1 it
-        // just wrote) and joined before the counter advances.  The branch runs at the lowest priority: the block scheduler
-        // stops feeding it while the chain's clusters are waiting for SMs, and it fills the SMs the chain leaves idle.
-        LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
-        LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
-        LIC360_CUDA(wf_launch_old(n.wf, 1, side));
-        LIC360_CUDA(cudaEventRecord(n.ev_join, side));
-    }
+    const bool fork = side != s;  // graph capture: overlap the old terms of the next step with the chain (see below)
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
     LIC360_CUDA(wf_launch_prev(n.wf, s));
     WF_DEBUG_SYNC("previous-wavefront kernel");
@@ -420,18 +411,33 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     LIC360_CUDA(wf_launch_chain(n.wf, s));
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
+    cudaStream_t rs = s;  // stream of the rows kernel
+    if (fork) {
+        // The old terms of step p+1 only read wavefronts <= p-1: they are launched right behind the chain kernel as its
+        // PROGRAMMATIC dependent -- they start once every chain CTA is resident (so the chain's clusters got their SMs
+        // first) and fill the SMs the chain leaves idle.  The rows kernel needs the chain's RESULTS, so it waits for the
+        // chain's completion on the side stream; both branches join before the step counter advances.
+        LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
+        LIC360_CUDA(wf_launch_old(n.wf, 1, s, true));
+        LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
+        rs = side;
+    }
     if (is_code)
-        gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, s>>>(n.wf.fc[12], c->levels_dev, n.idx_dev,
+        gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, rs>>>(n.wf.fc[12], c->levels_dev, n.idx_dev,
                                                  n.steps_dev, n.ctr_dev, n.rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
                                                  (float)(1. / sqrt(2.0)), n.done_dev, n.flag_host);
     else
-        imp_rows_wf_kernel<<<tgrid, 128, 0, s>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
+        imp_rows_wf_kernel<<<tgrid, 128, 0, rs>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
                                                  n.done_dev, n.flag_host);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
-    if (fork) LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_join, 0));
-    else LIC360_CUDA(wf_launch_old(n.wf, 1, s));
+    if (fork) {
+        LIC360_CUDA(cudaEventRecord(n.ev_join, side));
+        LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_join, 0));
+    } else {
+        LIC360_CUDA(wf_launch_old(n.wf, 1, s));
+    }
     WF_DEBUG_SYNC("old-term kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
     advance_kernel<<<1, 1, 0, s>>>(n.ctr_dev);
@@ -446,7 +452,7 @@ static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaGraph_t g;
     const long long l0 = g_launches;
     LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    static const bool overlap = getenv("LIC360_WF_OVERLAP") != nullptr;  // measured slower on B200 (the branch delays the chain clusters): off by default
+    static const bool overlap = getenv("LIC360_WF_NO_OVERLAP") == nullptr;
     const int rc = launch_step(c, n, is_code, s, overlap ? n.side : s, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &g);
     n.graph_nodes = (int)(g_launches - l0);

@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
     extern __shared__ float4 wf_part[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    // programmatic dependent launch: the old-term kernel of the next step may start as soon as every CTA of this kernel is
+    // resident (it does not read anything this kernel writes); without that launch attribute this is a no-op
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const StepDesc sd = net.steps[*net.ctr];
     const int HW = net.H * net.W;
     for (int l = 0; l < WF_LAYERS; l++) {
@@ -507,6 +510,9 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
     extern __shared__ float4 wf_wsm[];  // [2][rows_cap][WF_ROW_F4]
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    // programmatic dependent launch: the old-term kernel of the next step may start as soon as every CTA of this kernel is
+    // resident (it does not read anything this kernel writes); without that launch attribute this is a no-op
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const StepDesc sd = net.steps[*net.ctr];
     const int HW = net.H * net.W, par = sd.psum & 1;
     const int per = (sd.len + nc - 1) / nc;
@@ -624,6 +630,9 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
     extern __shared__ float4 wf_sm1[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
+    // programmatic dependent launch: the old-term kernel of the next step may start as soon as every CTA of this kernel is
+    // resident (it does not read anything this kernel writes); without that launch attribute this is a no-op
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const StepDesc sd = net.steps[*net.ctr];
     const int par = sd.psum & 1, d = sd.psum, len = sd.len;
     const int hmin = max(0, d - net.W + 1);
@@ -854,7 +863,9 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    int want = 16;
+    // many-group nets (3 clusters, old-term kernel running beside them): 8 CTAs each measured best; the single-group net
+    // has one cluster and splits output chunks: 16
+    int want = G > 1 ? 8 : 16;
     if (const char* s = getenv("LIC360_WF_CLUSTER")) want = std::max(1, std::min(16, atoi(s)));
     for (e.cluster = want;; e.cluster = 8) {
         int tasks_max = 0;
@@ -882,6 +893,9 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
             else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
         }
         if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
+        // The old-term kernel of the next step runs concurrently (programmatic dependent launch): claim the whole shared
+        // memory of the SM so that none of its CTAs lands next to a chain CTA and steals its issue slots.
+        if (!getenv("LIC360_WF_SHARE_SM")) e.chain_smem = std::max(e.chain_smem, (size_t)196 * 1024);
         if (e.chain_smem > chain_attr) {
             LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
             LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
@@ -929,17 +943,21 @@ cudaError_t wf_clear(const WfEngine& e, cudaStream_t s) {
     return cudaMemsetAsync(e.pbuf, 0, e.pbuf_f4 * sizeof(float4), s);
 }
 
-cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s) {
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic) {
     const WfNetDev& n = e.dev;
-    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, WF_OLD_WARPS);
-    const cudaError_t stale = cudaGetLastError();
-    wf_old_kernel<<<grid, block, e.old_smem, s>>>(n, e.maps, dp);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets);
+    cfg.blockDim = dim3(32, WF_OLD_WARPS);
+    cfg.dynamicSmemBytes = e.old_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start once the previous kernel's CTAs have all
+    attr[0].val.programmaticStreamSerializationAllowed = 1;          // executed griddepcontrol.launch_dependents
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic ? 1 : 0;
     g_launches++;
-    const cudaError_t r = cudaGetLastError();
-    if (r != cudaSuccess || stale != cudaSuccess)
-        fprintf(stderr, "lic360: wf_old_kernel launch grid (%u,%u,%u) block (%u,%u) smem %zu -> %s (stale: %s)\n", grid.x, grid.y, grid.z,
-                block.x, block.y, e.old_smem, cudaGetErrorString(r), cudaGetErrorString(stale));
-    return r;
+    return cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp);
 }
 
 cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s) {

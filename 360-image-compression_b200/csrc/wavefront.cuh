@@ -66,7 +66,8 @@ void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const fl
 void wf_free(WfEngine& e);
 const void* wf_old_kernel_ptr();  // to give the old-term kernel node its own (lowest) priority in the step graph
 cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)
-cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s);       // P of step *ctr + dp, all layers
+// P of step *ctr + dp, all layers.  programmatic: launch as a programmatic dependent of the previous kernel in the stream
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic = false);
 cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s);              // P + R of step *ctr, all layers
 cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s);             // the 12-layer chain of step *ctr
 
