@@ -291,6 +291,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": old_launch_us, "launches_per_decode": n_old,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic_note": prof.get("note"), "traffic_step_algorithmic_bytes": prof.get("algorithmic_bytes_this_step"),
                 "kernel_ms_per_decode": {"code": kt, "importance": kt_imp},
                 "note": "avg launch = CUDA-event time around every wf_old_kernel launch of one serialized decode on the codec stream (DESIGN.md s5)"}
     line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
