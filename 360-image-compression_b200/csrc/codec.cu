@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <sched.h>
 #include <thread>
 #include <cmath>
 #include <vector>
@@ -683,6 +684,7 @@ static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
+        if ((spins & 0x7F) == 0) sched_yield();  // several ranks / images per box: do not starve the other polling threads
     }
     return LIC360_OK;
 }
@@ -728,6 +730,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
 #if defined(__x86_64__)
                 __builtin_ia32_pause();
 #endif
+                if ((spins & 0x1F) == 0) sched_yield();
             }
         }
         if (c->mode == 0) {

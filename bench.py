@@ -231,7 +231,7 @@ def main():
     # the host arithmetic coder of one image overlaps the GPU steps of the other
     piped_ms = None
     try:
-        nfly = max(2, int(os.environ.get("LIC360_BENCH_IN_FLIGHT", "4")))
+        nfly = max(2, int(os.environ.get("LIC360_BENCH_IN_FLIGHT", "4" if world == 1 else "2")))  # each image has 2 polling host threads
         codecs = [codec] + [pl.FusedCodec(params, H=H, W=W, gid=local_rank) for _ in range(nfly - 1)]
         for cd in codecs:
             cd.decode(*cd.encode(tq, tm, tl))
