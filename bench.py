@@ -231,6 +231,8 @@ def main():
     # the host arithmetic coder of one image overlaps the GPU steps of the other
     piped_ms = None
     try:
+        if world > 1:
+            raise RuntimeError("single-GPU figure only (the host cores of the box are shared by all ranks)")
         nfly = max(2, int(os.environ.get("LIC360_BENCH_IN_FLIGHT", "4" if world == 1 else "2")))  # each image has 2 polling host threads
         codecs = [codec] + [pl.FusedCodec(params, H=H, W=W, gid=local_rank) for _ in range(nfly - 1)]
         for cd in codecs:
