@@ -82,6 +82,9 @@ struct lic360_codec {
 
 namespace lic360 {
 
+WF_TRACE_DECL
+static void codec_trace_set(unsigned long long* buf) { cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf)); }
+
 // ------------------------------------------------------------------------------------------------ kernels
 // code stream encoder input: x = (code - 3.5) * mask replicated for the 3 nets (lic360_demo.py:130-131)
 __global__ void prep_code_kernel(const float* __restrict__ code, const float* __restrict__ mask, float* __restrict__ x,
@@ -183,6 +186,7 @@ __global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __res
                                     int G, int H, int W, int D, int HS, int Dp, int Hp, float bias, float scale, int rep,
                                     float* __restrict__ keep) {
     const int c = *ctr;
+    if (G > 1 && threadIdx.x == 0) WF_TRACE_MIN(c, WF_TR_SCATTER);
     if (c == 0) return;
     const StepDesc d = steps[c - 1];
     const int HW = H * W;
@@ -220,6 +224,7 @@ __device__ __forceinline__ void rows_done(int* done, volatile int* flag, int ste
             *done = 0;
             __threadfence_system();
             *flag = step + 1;
+            if (gridDim.x > 4) WF_TRACE_MAX(step, WF_TR_ROWS1);
         }
     }
 }
@@ -234,6 +239,7 @@ __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __r
                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
                                    int G, int H, int W, int Dp, int Hp, float s2, int* done, int* flag) {
     const int step = *ctr;
+    if (threadIdx.x == 0) WF_TRACE_MIN(step, WF_TR_ROWS0);
     const StepDesc d = steps[step];
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = gt >> 3, j = gt & 7;
@@ -778,6 +784,19 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     c->t_host_coder = 0; c->t_gpu_wait = 0; c->t_gpu_steps = 0; c->t_gpu_steps_imp = 0; c->t_imp = 0;
     c->imp_ready.store(0);
     c->abort_flag.store(0);
+    // debug timeline of the code stream (LIC360_WF_TRACE=1): %globaltimer stamps per step, summarised on stderr
+    unsigned long long* trace_dev = nullptr;
+    const int tr_steps = c->code.nsteps + 2;
+    if (getenv("LIC360_WF_TRACE")) {
+        std::vector<unsigned long long> init((size_t)tr_steps * WF_TR_SLOTS);
+        for (int p = 0; p < tr_steps; p++)
+            for (int k = 0; k < WF_TR_SLOTS; k++)
+                init[(size_t)p * WF_TR_SLOTS + k] = (k == WF_TR_CHAIN1 || k == WF_TR_ROWS1 || k == WF_TR_OLD1) ? 0ull : ~0ull;
+        LIC360_CUDA(cudaMalloc(&trace_dev, init.size() * 8));
+        LIC360_CUDA(cudaMemcpy(trace_dev, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+        wf_trace_set(trace_dev);
+        codec_trace_set(trace_dev);
+    }
     if (c->mode == 0) {  // both step graphs exist before the second host thread starts
         rc = build_step_graph(c, c->imp, false);
         if (rc == LIC360_OK) rc = build_step_graph(c, c->code, true);
@@ -820,6 +839,28 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
                                                              c->code.wf.dev.Dp, c->code.wf.dev.Hp, 3.5f);
     LAUNCH_CHECK();
     LIC360_CUDA(cudaStreamSynchronize(s));
+    if (trace_dev) {
+        std::vector<unsigned long long> tr((size_t)tr_steps * WF_TR_SLOTS);
+        cudaMemcpy(tr.data(), trace_dev, tr.size() * 8, cudaMemcpyDeviceToHost);
+        wf_trace_set(nullptr);
+        codec_trace_set(nullptr);
+        cudaFree(trace_dev);
+        const char* names[WF_TR_SLOTS] = {"scatter start", "prev start", "chain start", "chain end", "rows start", "rows flag", "old start", "old end"};
+        for (int w0 = 0; w0 < 2; w0++) {  // two windows: while the importance stream still runs / after it finished
+            const int pa = w0 == 0 ? 20 : 140, pb = w0 == 0 ? 80 : 220;
+            double acc[WF_TR_SLOTS] = {0}, period = 0;
+            int cnt = 0;
+            for (int p = pa; p < pb && p + 1 < c->code.nsteps; p++) {
+                const unsigned long long* r = &tr[(size_t)p * WF_TR_SLOTS];
+                for (int k = 0; k < WF_TR_SLOTS; k++) acc[k] += (double)(long long)(r[k] - r[0]) * 1e-3;
+                period += (double)(long long)(tr[(size_t)(p + 1) * WF_TR_SLOTS] - r[0]) * 1e-3;
+                cnt++;
+            }
+            fprintf(stderr, "lic360 trace, code-stream steps %d..%d: period %.1f us;", pa, pb, period / cnt);
+            for (int k = 1; k < WF_TR_SLOTS; k++) fprintf(stderr, " %s +%.1f;", names[k], acc[k] / cnt);
+            fprintf(stderr, "\n");
+        }
+    }
     c->t_host_coder = c->code.t_host_coder + c->imp.t_host_coder;
     c->t_gpu_wait = c->code.t_gpu_wait;
     c->t_total = ms_since(t0);

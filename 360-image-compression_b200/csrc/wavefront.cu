@@ -23,6 +23,9 @@ namespace cg = cooperative_groups;
 
 namespace lic360 {
 
+WF_TRACE_DECL
+void wf_trace_set(unsigned long long* buf) { cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf)); }
+
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
 // The inner (h) coordinate of a TMA box must be 16-byte aligned (4 floats; an unaligned start faults with "illegal
 // instruction" on sm_100, tools/tma_probe.cu), so the box starts at (hbase - 2) rounded down to 4 and is 40 wide.
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
     extern __shared__ unsigned char wf_raw[];
     const WfTile t = wf_tile(net, dp);
     if (!t.ok) return;  // CTA-uniform
+    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum - dp, WF_TR_OLD0);
     const WfLayerDev& L = net.L[t.l];
     const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
     unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
         }
         L.pbuf[t.psum & 1][(((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h] = P;
     }
+    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(t.psum - dp, WF_TR_OLD1);
 }
 
 // ------------------------------------------------------------------------------------------------ R / Q terms
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
     extern __shared__ float4 wf_psm[];  // [TAPS * cin_g (<= wcap)] weights, then [nqb][32] partials
     const WfTile t = wf_tile(net, 0);
     if (!t.ok) return;
+    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum, WF_TR_PREV);
     const WfLayerDev& L = net.L[t.l];
     const int lane = threadIdx.x, jq = threadIdx.y, tid = jq * 32 + lane, nthr = blockDim.x * blockDim.y;
     const int cin_g = L.cin_g, G = net.G, Hp = net.Hp;
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const StepDesc sd = net.steps[*net.ctr];
     const int HW = net.H * net.W, par = sd.psum & 1;
+    if (threadIdx.x == 0) WF_TRACE_MIN(sd.psum, WF_TR_CHAIN0);
     const int per = (sd.len + nc - 1) / nc;
     const int i0 = min(sd.len, rank * per), i1 = min(sd.len, i0 + per), nloc = i1 - i0;
     // plan order is diagonal-major, so the output groups of this CTA's items are the contiguous range [tc_lo, tc_hi]
@@ -615,6 +622,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
             else __syncthreads();
         }
     }
+    if (threadIdx.x == 0) WF_TRACE_MAX(sd.psum, WF_TR_CHAIN1);
 }
 
 // Chain for single-group nets (the importance stream: G = 1, 144 channels).  A step is ONE anti-diagonal (<= min(H,W)

@@ -77,6 +77,28 @@ constexpr int WF_GPAD = 5;
 __host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int G, int cpg, int n, int d, int g, int h) {
     return ((((size_t)n * Dp + d + 4) * (G + 2 * WF_GPAD) + g + WF_GPAD) * Hp + h + 2) * cpg;
 }
+// Debug timeline (LIC360_WF_TRACE=1): per step 8 slots of %globaltimer stamps.  Each translation unit has its own copy of
+// the device pointer (no relocatable device code); wf_trace_set() / codec_trace_set() point both at the same buffer.
+enum { WF_TR_SCATTER = 0, WF_TR_PREV, WF_TR_CHAIN0, WF_TR_CHAIN1, WF_TR_ROWS0, WF_TR_ROWS1, WF_TR_OLD0, WF_TR_OLD1, WF_TR_SLOTS };
+void wf_trace_set(unsigned long long* buf);
+#define WF_TRACE_DECL static __device__ unsigned long long* g_wf_trace = nullptr;
+#define WF_TRACE_MIN(step, slot)                                                                          \
+    do {                                                                                                  \
+        if (g_wf_trace) {                                                                                 \
+            unsigned long long t_;                                                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+            atomicMin(g_wf_trace + (size_t)(step) * WF_TR_SLOTS + (slot), t_);                            \
+        }                                                                                                 \
+    } while (0)
+#define WF_TRACE_MAX(step, slot)                                                                          \
+    do {                                                                                                  \
+        if (g_wf_trace) {                                                                                 \
+            unsigned long long t_;                                                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+            atomicMax(g_wf_trace + (size_t)(step) * WF_TR_SLOTS + (slot), t_);                            \
+        }                                                                                                 \
+    } while (0)
+
 __host__ __device__ inline size_t wf_fp_index(int D, int HS, int C, int n, int c, int d, int h) {
     return (((size_t)n * C + c) * D + d) * HS + h;
 }
