@@ -54,6 +54,7 @@ struct NetDesc {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof[6] = {nullptr};
     int* ctr_dev = nullptr;             // current wavefront step (device counter)
     int* done_dev = nullptr;            // CTA counter of the rows kernel
+    int* sync_dev = nullptr;            // code stream: monotone cross-cluster counter of the chain kernel's rows phase
     int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
     uint16_t* rows_dev = nullptr;       // encode: all rows of the stream
     uint16_t* rows_host = nullptr;      // pinned
@@ -93,19 +94,6 @@ __global__ void prep_code_kernel(const float* __restrict__ code, const float* __
         const float v = (code[i] - bias) * mask[i];
         x[i] = v; x[i + n] = v; x[i + 2 * n] = v;
     }
-}
-
-__device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst) {
-    uint32_t ovf = 0;
-    uint16_t w[8];
-#pragma unroll
-    for (int j = 1; j <= 7; j++) {
-        const uint32_t v = (uint32_t)(int)o[j];
-        w[j - 1] = (uint16_t)(v & 0xFFFF);
-        ovf |= ((v >> 16) & 1u) << (j - 1);
-    }
-    w[7] = (uint16_t)((sym & 7) | (maskbit << 8) | (ovf << 9));
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
 }
 
 // y: (3, G*3, H, W) outputs of [weight_net, delta_net, mean_net]; one thread = one symbol (tc, k) in plan order.
@@ -412,10 +400,18 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("scatter kernel");
     const bool fork = side != s;  // graph capture: overlap the old terms of the next step with the chain (see below)
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
-    LIC360_CUDA(wf_launch_prev(n.wf, s));
-    WF_DEBUG_SYNC("previous-wavefront kernel");
+    LIC360_CUDA(wf_launch_prev(n.wf, 0, 0, 1, s));  // layer 0 only: its taps read the symbols scattered a moment ago
+    WF_DEBUG_SYNC("previous-wavefront kernel (layer 0)");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[2], s));
-    LIC360_CUDA(wf_launch_chain(n.wf, s));
+    // the chain; for the code stream it also emits the CDF rows of the step and raises the host flag
+    WfRows rows;
+    memset(&rows, 0, sizeof(rows));
+    const bool fused_rows = is_code && n.wf.chain4 && !getenv("LIC360_WF_ROWS_KERNEL");
+    if (fused_rows) {
+        rows.rows = n.rows_step_host; rows.levels = c->levels_dev; rows.done = n.done_dev; rows.flag = n.flag_host;
+        rows.sync = n.sync_dev; rows.s2 = (float)(1. / sqrt(2.0)); rows.enabled = 1;
+    }
+    LIC360_CUDA(wf_launch_chain(n.wf, s, fused_rows ? &rows : nullptr));
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
     cudaStream_t rs = s;  // stream of the rows kernel
@@ -429,15 +425,20 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
         LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
         rs = side;
     }
-    if (is_code)
+    if (fused_rows) {
+    } else if (is_code)
         gmm_rows_wf_kernel<<<(n.max_len * 8 + 127) / 128, 128, 0, rs>>>(n.wf.fc[12], c->levels_dev, n.idx_dev,
                                                  n.steps_dev, n.ctr_dev, n.rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
                                                  (float)(1. / sqrt(2.0)), n.done_dev, n.flag_host);
     else
         imp_rows_wf_kernel<<<tgrid, 128, 0, rs>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
                                                  n.done_dev, n.flag_host);
-    LAUNCH_CHECK();
+    if (!fused_rows) LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
+    // previous-wavefront terms of layers 1..11 for step p+1 (the activations of wavefront p are final): behind the rows
+    // kernel, i.e. underneath the host decoder instead of on the critical path
+    LIC360_CUDA(wf_launch_prev(n.wf, 1, 1, WF_LAYERS, rs));
+    WF_DEBUG_SYNC("previous-wavefront kernel (layers 1..11 of the next step)");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
     if (fork) {
         LIC360_CUDA(cudaEventRecord(n.ev_join, side));
@@ -509,6 +510,7 @@ static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int pri
     for (int i = 0; i < 6; i++) LIC360_CUDA(cudaEventCreate(&n.ev_prof[i]));
     LIC360_CUDA(cudaMalloc(&n.ctr_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.sync_dev, sizeof(int)));
     LIC360_CUDA(cudaHostAlloc(&n.flag_host, sizeof(int), cudaHostAllocMapped));
     n.coder = lic360_coder_create("", fill);
     return n.coder ? LIC360_OK : LIC360_ERR_ARG;
@@ -523,7 +525,7 @@ static int ctx_buffers(NetDesc& n) {
 }
 
 static void ctx_free(NetDesc& n) {
-    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFreeHost(n.flag_host);
+    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host);
     cudaFree(n.rows_dev); cudaFreeHost(n.rows_host); cudaFreeHost(n.rows_step_host); cudaFreeHost(n.syms_host);
     if (n.ev_fork) cudaEventDestroy(n.ev_fork);
     if (n.ev_join) cudaEventDestroy(n.ev_join);
@@ -724,6 +726,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     LIC360_CUDA(wf_clear(n.wf, s));
     LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0, sizeof(int), s));
     LIC360_CUDA(cudaMemsetAsync(n.done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.sync_dev, 0, sizeof(int), s));
     LIC360_CUDA(wf_launch_old(n.wf, 0, s));  // old terms of step 0 (all zero, but it keeps the schedule uniform)
     if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;

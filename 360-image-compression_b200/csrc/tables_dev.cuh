@@ -3,6 +3,7 @@
 // Bit-exact tier: every float/double promotion of the reference expressions is kept literally
 // (entropy_gmm_table_cuda.cu:29-107, entropy_table_cuda.cu:24-76); do not compile with --use_fast_math.
 #pragma once
+#include <stdint.h>
 
 namespace lic360 {
 
@@ -75,5 +76,20 @@ __device__ __forceinline__ void entropy_row(float* o, int w, float total) {
     o[w] = total;
     fixup_row(o, w, false);
 }
+
+// packed code-stream row (coder_internal.h): 7 x u16 low words of T[1..7] + meta = sym | mask << 8 | overflow bits << 9
+__device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst) {
+    uint32_t ovf = 0;
+    uint16_t w[8];
+#pragma unroll
+    for (int j = 1; j <= 7; j++) {
+        const uint32_t v = (uint32_t)(int)o[j];
+        w[j - 1] = (uint16_t)(v & 0xFFFF);
+        ovf |= ((v >> 16) & 1u) << (j - 1);
+    }
+    w[7] = (uint16_t)((sym & 7) | (maskbit << 8) | (ovf << 9));
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
+}
+
 
 }  // namespace lic360

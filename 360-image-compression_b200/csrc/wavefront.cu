@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <vector>
 #include "conv_dev.cuh"
+#include "tables_dev.cuh"
 #include "wavefront.cuh"
 
 namespace cg = cooperative_groups;
@@ -74,9 +75,9 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, int byt
 //   blockIdx.z -> (layer, net)
 struct WfTile { int l, n, kc, psum, d, hbase, hmax, tc; bool ok; };
 
-__device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp) {
+__device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp, int l0 = 0) {
     WfTile t;
-    t.l = blockIdx.z / net.nsets;
+    t.l = l0 + blockIdx.z / net.nsets;
     t.n = blockIdx.z % net.nsets;
     t.kc = blockIdx.y;
     t.psum = *net.ctr + dp;
@@ -273,16 +274,16 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
     return u;
 }
 
-// previous-wavefront terms of ALL layers of step *ctr: pbuf <- P + R.  Same CTA geometry as wf_old_kernel, so a CTA
+// previous-wavefront terms R of layers [l0, ..) of step *ctr + dp -> rbuf.  Same CTA geometry as wf_old_kernel, so a CTA
 // has ONE output group: its row of class-0 weights ([tap][cin_g] float4, only the taps that select an existing group)
 // is staged in shared memory with cp.async; warp jq = canonical 16-channel block jq of the group, and the activation
 // loads of a whole 4-channel chunk (all taps) are in flight before its first FMA.
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant__ WfNetDev net, int wcap) {
+__global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant__ WfNetDev net, int wcap, int dp, int l0) {
     extern __shared__ float4 wf_psm[];  // [TAPS * cin_g (<= wcap)] weights, then [nqb][32] partials
-    const WfTile t = wf_tile(net, 0);
+    const WfTile t = wf_tile(net, dp, l0);
     if (!t.ok) return;
-    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum, WF_TR_PREV);
+    if (net.G > 1 && dp == 0 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum, WF_TR_PREV);
     const WfLayerDev& L = net.L[t.l];
     const int lane = threadIdx.x, jq = threadIdx.y, tid = jq * 32 + lane, nthr = blockDim.x * blockDim.y;
     const int cin_g = L.cin_g, G = net.G, Hp = net.Hp;
@@ -395,10 +396,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
         r.x = 0.f + r.x; r.y = 0.f + r.y; r.z = 0.f + r.z; r.w = 0.f + r.w;  // R = 0 + r_0, as everywhere else
     }
     if (!valid) return;
-    float4* pp = L.pbuf[t.psum & 1] + (((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h;
-    float4 P = *pp;
-    P.x = P.x + r.x; P.y = P.y + r.y; P.z = P.z + r.z; P.w = P.w + r.w;
-    *pp = P;
+    L.rbuf[t.psum & 1][(((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h] = r;
 }
 
 // ------------------------------------------------------------------------------------------------ the 12-layer chain
@@ -436,7 +434,9 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
             const int h = __ldg(net.idx + k), w = __ldg(net.idx + k + HW);
             const int d = h + w, tc = sd.psum - d;
             // independent loads first: P + R, bias, slope, residual
-            const float4 pr = __ldg(L.pbuf[sd.psum & 1] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+            const size_t pi = (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h;
+            float4 pr = __ldg(L.pbuf[sd.psum & 1] + pi);
+            { const float4 rr = __ldg(L.rbuf[sd.psum & 1] + pi); pr.x = pr.x + rr.x; pr.y = pr.y + rr.y; pr.z = pr.z + rr.z; pr.w = pr.w + rr.w; }
             const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h) + kc * 4;
             const int o0 = tc * L.cout_g + kc * 4;
             float bs[4], sl[4], rs[4];
@@ -496,11 +496,12 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
 // Per layer that leaves: cluster barrier -> one L2 round trip -> 400 FMAs against shared-memory weights -> stores.
 constexpr int WF_ROW_F4 = TAPS * 4;  // float4 per (output group) row of same-wavefront weights when cin_g == 4
 
-struct WfPre { float4 pr; float bs[4], sl[4], rs[4]; };
+struct WfPre { float4 pr, rr; float bs[4], sl[4], rs[4]; };  // P and R: added where they are consumed, a layer later
 
 __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const WfLayerDev& L, int n, int par, int d, int h, int tc,
                                                    WfPre& p) {
     p.pr = __ldg(L.pbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
+    p.rr = __ldg(L.rbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
     const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h);
     const int o0 = tc * L.cout_g;
 #pragma unroll
@@ -512,7 +513,66 @@ __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const Wf
     }
 }
 
-__global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant__ WfNetDev net, int nc, int rows_cap) {
+// CDF rows of the step (TileExtract + EntropyGmmTable fused) at the end of the chain kernel: a row needs the outputs of all
+// three nets, so the clusters meet at a monotone global counter first (every CTA of the grid is resident or becomes
+// resident without needing anything from the waiting ones: no deadlock).  A separate, non-inlined function: its register
+// needs (erff, the 9-bin row) stay out of the chain's layer loop.
+__device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& rows, int psum, int start, int len, int tid, int nt) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(rows.sync, 1);
+        const int target = (psum + 1) * (int)gridDim.x;
+        while (*reinterpret_cast<volatile int*>(rows.sync) < target) {}
+        __threadfence();
+        WF_TRACE_MIN(psum, WF_TR_ROWS0);
+    }
+    __syncthreads();
+    const int G = net.G, H = net.H, W = net.W, HW = H * W;
+    const float* y = net.L[WF_LAYERS - 1].oc;
+    const int total = ((len * 8 + 31) >> 5) << 5;  // whole warps: 8 lanes per symbol, lane j computes bin j
+    for (int gt = blockIdx.x * nt + tid; gt < total; gt += (int)gridDim.x * nt) {
+        const int li = gt >> 3, j = gt & 7;
+        const bool live = li < len;
+        float bin = 0.f;
+        int th = 0, tw = 0, tc = 0;
+        if (live) {
+            th = __ldg(net.idx + start + li); tw = __ldg(net.idx + start + li + HW);
+            tc = psum - th - tw;
+            float wv[3], dv[3], mv[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                wv[i] = __ldcg(y + wf_fc_index(net.Dp, net.Hp, G, 3, 0, th + tw, tc, th) + i);
+                dv[i] = __ldcg(y + wf_fc_index(net.Dp, net.Hp, G, 3, 1, th + tw, tc, th) + i);
+                mv[i] = __ldcg(y + wf_fc_index(net.Dp, net.Hp, G, 3, 2, th + tw, tc, th) + i);
+            }
+            gmm_prep(wv, dv, 3, 1e-6f);
+            if (j >= 1) bin = gmm_bin_value(wv, dv, mv, j, 3, 3.5f, 65536.f, rows.s2);
+        }
+        float o[9];
+        o[0] = 0.f; o[8] = 65536.f;
+#pragma unroll
+        for (int k = 1; k < 8; k++) o[k] = __shfl_sync(0xffffffffu, bin, (tid & 24) + k);
+        if (live && j == 0) {
+            fixup_row(o, 8, true);
+            const int lvl = (int)(rows.levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
+            pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows.rows + (size_t)li * 8);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        if (atomicAdd(rows.done, 1) == (int)gridDim.x - 1) {
+            *rows.done = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile int*>(rows.flag) = psum + 1;
+            WF_TRACE_MAX(psum, WF_TR_ROWS1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant__ WfNetDev net, int nc, int rows_cap,
+                                                         const __grid_constant__ WfRows rows) {
     extern __shared__ float4 wf_wsm[];  // [2][rows_cap][WF_ROW_F4]
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
@@ -594,7 +654,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                     }
             }
             const float Q[4] = {0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w};  // Q = 0 + q_0 (one canonical block)
-            const float PR[4] = {p.pr.x, p.pr.y, p.pr.z, p.pr.w};
+            const float PR[4] = {p.pr.x + p.rr.x, p.pr.y + p.rr.y, p.pr.z + p.rr.z, p.pr.w + p.rr.w};
             const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h);
             float v[4];
 #pragma unroll
@@ -623,6 +683,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
         }
     }
     if (threadIdx.x == 0) WF_TRACE_MAX(sd.psum, WF_TR_CHAIN1);
+    if (rows.enabled) wf_chain4_rows(net, rows, sd.psum, sd.start, sd.len, tid, nt);
 }
 
 // Chain for single-group nets (the importance stream: G = 1, 144 channels).  A step is ONE anti-diagonal (<= min(H,W)
@@ -669,6 +730,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
         if (tid >= kn * len) return;
         const int kc = kc0 + tid / len, h = hmin + tid % len;
         pre.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+        pre.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
         const size_t fc = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -734,6 +796,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
             WfPre p = pre;
             if (it != tid) {  // further slots (more items than threads): nothing was prefetched
                 p.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+                p.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
                 const size_t fcr = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -749,7 +812,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
                     const float4 v = part[((size_t)k * nqb_max + j) * lenp + pos];
                     Q[0] = Q[0] + v.x; Q[1] = Q[1] + v.y; Q[2] = Q[2] + v.z; Q[3] = Q[3] + v.w;
                 }
-            const float PR[4] = {p.pr.x, p.pr.y, p.pr.z, p.pr.w};
+            const float PR[4] = {p.pr.x + p.rr.x, p.pr.y + p.rr.y, p.pr.z + p.rr.z, p.pr.w + p.rr.w};
             const size_t fc = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
             float v[4];
 #pragma unroll
@@ -813,7 +876,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         L.cin_g = L.Cin / G; L.cout_g = L.Cout / G; L.cpg4 = (L.cout_g + 3) / 4; L.nchunk = G * L.cpg4;
         L.nblk = (L.Cin + CB - 1) / CB; L.nqb = (L.cin_g + CB - 1) / CB; L.has_q = l != 0;
         e.cpg4_max = std::max(e.cpg4_max, L.cpg4); e.nblk_max = std::max(e.nblk_max, L.nblk); e.nqb_max = std::max(e.nqb_max, L.nqb);
-        pb += 2 * (size_t)nsets * L.cpg4 * n.D * n.HS;
+        pb += 4 * (size_t)nsets * L.cpg4 * n.D * n.HS;  // P and R, two step parities each
     }
     if (e.nblk_max > 32 || e.nqb_max > 32) { set_error("wavefront engine: too many channels"); return LIC360_ERR_ARG; }
     for (int i = 0; i <= WF_LAYERS; i++) {
@@ -835,6 +898,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         L.oc = e.fc[l + 1];
         L.rc = (l >= 2 && l <= 10 && (l % 2) == 0) ? e.fc[l - 1] : nullptr;  // conv2 of residual block b = layer 2b (y + x)
         for (int par = 0; par < 2; par++) { L.pbuf[par] = pp; pp += (size_t)nsets * L.cpg4 * n.D * n.HS; }
+        for (int par = 0; par < 2; par++) { L.rbuf[par] = pp; pp += (size_t)nsets * L.cpg4 * n.D * n.HS; }
     }
     // TMA descriptors: FP frame of layer l as a 3-D tensor {HS, D, nsets*Cin}, box {40, 9, 4}, zero fill outside
     EncodeTiledFn enc = encode_tiled_fn();
@@ -968,16 +1032,21 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     return cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp);
 }
 
-cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s) {
+cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream_t s) {
     const WfNetDev& n = e.dev;
-    dim3 grid(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets), block(32, e.nqb_max);
-    if (e.nqb_max <= 10) wf_prev_kernel<320><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap);
-    else wf_prev_kernel<1024><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap);
+    int cpg4 = 0, nqb = 0;
+    for (int l = l0; l < l1; l++) { cpg4 = std::max(cpg4, n.L[l].cpg4); nqb = std::max(nqb, n.L[l].nqb); }
+    dim3 grid(n.ndiag * n.parts, cpg4, (l1 - l0) * n.nsets), block(32, nqb);
+    if (e.nqb_max <= 10) wf_prev_kernel<320><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap, dp, l0);
+    else wf_prev_kernel<1024><<<grid, block, e.prev_smem, s>>>(n, e.prev_wcap, dp, l0);
     g_launches++;
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s) {
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows) {
+    WfRows r;
+    memset(&r, 0, sizeof(r));
+    if (rows && e.chain4) r = *rows;
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -991,7 +1060,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
-    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G);
+    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r);
     if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }

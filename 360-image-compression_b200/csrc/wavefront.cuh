@@ -28,7 +28,8 @@ struct WfLayerDev {
     const float* wq;     // R / Q weights    [cls][set][chunk][tap][c]  float4
     const float* bias;   // [set][Cout]
     const float* slope;  // [set][Cout] or nullptr (no PReLU)
-    float4* pbuf[2];     // old-term sums P, then P + R, by step parity: [set][kc][D][HS]
+    float4* pbuf[2];     // old-term sums P by step parity: [set][kc][D][HS]
+    float4* rbuf[2];     // previous-wavefront sums R by step parity, same shape
     int Cin, Cout, cin_g, cout_g, cpg4, nchunk, nblk, nqb, has_q, pad;
 };
 
@@ -38,6 +39,17 @@ struct WfNetDev {
     const int* ctr;         // current step (device counter, advanced at the end of every step graph)
     const int32_t* idx;     // index plan (row plane, column plane), code_contex_cuda.cu:11-32
     int nsets, G, H, W, D, HS, Dp, Hp, nsteps, parts, ndiag, pad;
+};
+
+// code stream: the CDF rows of the step are produced at the end of the chain kernel (no extra launch on the critical path)
+struct WfRows {
+    uint16_t* rows;       // mapped pinned: packed rows of the step
+    const float* levels;  // decoded importance levels (mask bit = Imp2mask + Dtow of the symbol's 2x2 cell)
+    int* done;            // CTA counter of the rows phase
+    int* flag;            // mapped pinned: step + 1 once the rows are written
+    int* sync;            // monotone counter: all nets have finished layer 11 of step p when it reaches (p + 1) * gridDim.x
+    float s2;
+    int enabled;
 };
 
 struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer, box {40 h, 9 d, 4 c}
@@ -68,8 +80,10 @@ const void* wf_old_kernel_ptr();  // to give the old-term kernel node its own (l
 cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)
 // P of step *ctr + dp, all layers.  programmatic: launch as a programmatic dependent of the previous kernel in the stream
 cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic = false);
-cudaError_t wf_launch_prev(const WfEngine& e, cudaStream_t s);              // P + R of step *ctr, all layers
-cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s);             // the 12-layer chain of step *ctr
+// R of step *ctr + dp for layers [l0, l1): layer 0 at dp = 0 right after the scatter (it reads the symbols just decoded),
+// layers 1..11 at dp = 1 right after the chain (underneath the host decoder)
+cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream_t s);
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows = nullptr);  // the 12-layer chain of step *ctr
 
 // first channel of group g at (d, h); cpg = channels per group of that frame.  The group axis carries WF_GPAD zero
 // groups on each side: a tap of the R / Q terms may select group -5 .. G+3, which then reads zeros instead of needing a test.
