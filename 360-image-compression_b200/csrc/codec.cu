@@ -400,13 +400,15 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("scatter kernel");
     const bool fork = side != s;  // graph capture: overlap the old terms of the next step with the chain (see below)
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
-    LIC360_CUDA(wf_launch_prev(n.wf, 0, 0, 1, s));  // layer 0 only: its taps read the symbols scattered a moment ago
-    WF_DEBUG_SYNC("previous-wavefront kernel (layer 0)");
+    const bool fused_rows = is_code && n.wf.chain4 && !getenv("LIC360_WF_ROWS_KERNEL");
+    if (!(fused_rows && n.wf.r0_inline)) {  // else the chain kernel evaluates them in its prologue
+        LIC360_CUDA(wf_launch_prev(n.wf, 0, 0, 1, s));  // layer 0 only: its taps read the symbols scattered a moment ago
+        WF_DEBUG_SYNC("previous-wavefront kernel (layer 0)");
+    }
     if (ev) LIC360_CUDA(cudaEventRecord(ev[2], s));
     // the chain; for the code stream it also emits the CDF rows of the step and raises the host flag
     WfRows rows;
     memset(&rows, 0, sizeof(rows));
-    const bool fused_rows = is_code && n.wf.chain4 && !getenv("LIC360_WF_ROWS_KERNEL");
     if (fused_rows) {
         rows.rows = n.rows_step_host; rows.levels = c->levels_dev; rows.done = n.done_dev; rows.flag = n.flag_host;
         rows.sync = n.sync_dev; rows.s2 = (float)(1. / sqrt(2.0)); rows.enabled = 1;

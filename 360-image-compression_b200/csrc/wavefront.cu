@@ -513,6 +513,33 @@ __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const Wf
     }
 }
 
+// Previous-wavefront terms R of one item of LAYER 0 when it has one channel per group (the code stream's first layer):
+// they read the symbols the host decoded a moment ago, so they cannot be computed a step ahead like the other layers'.
+// 25 activations and 25 weight vectors, all in flight together; groups outside [0, G) read the zero padding of the group
+// axis and carry zero weights.  Non-inlined: runs once per step, outside the layer loop.
+__device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d, int h, int tc) {
+    const WfLayerDev& L = net.L[0];
+    const int GP = net.G + 2 * WF_GPAD;
+    const float* xr = L.xc + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
+    const size_t srow = (size_t)(GP - 1) * net.Hp;
+    const float4* w = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + tc) * TAPS;
+    float xv[TAPS];
+    float4 wv[TAPS];
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            xv[kh * 5 + kw] = __ldg(xr + (kh + kw) * srow + kh);
+            wv[kh * 5 + kw] = __ldg(w + kh * 5 + kw);
+        }
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < TAPS; t++) {
+        u.x = fmaf(xv[t], wv[t].x, u.x); u.y = fmaf(xv[t], wv[t].y, u.y); u.z = fmaf(xv[t], wv[t].z, u.z); u.w = fmaf(xv[t], wv[t].w, u.w);
+    }
+    return make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0 (one canonical block)
+}
+
 // CDF rows of the step (TileExtract + EntropyGmmTable fused) at the end of the chain kernel: a row needs the outputs of all
 // three nets, so the clusters meet at a monotone global counter first (every CTA of the grid is resident or becomes
 // resident without needing anything from the waiting ones: no deadlock).  A separate, non-inlined function: its register
@@ -572,7 +599,7 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
 }
 
 __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant__ WfNetDev net, int nc, int rows_cap,
-                                                         const __grid_constant__ WfRows rows) {
+                                                         const __grid_constant__ WfRows rows, int r0_inline) {
     extern __shared__ float4 wf_wsm[];  // [2][rows_cap][WF_ROW_F4]
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
@@ -602,7 +629,10 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
         tc0 = sd.psum - d0;
     }
     WfPre pre;
-    if (has0) wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
+    if (has0) {
+        wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
+        if (r0_inline) pre.rr = wf_r_layer0_c1(net, n, d0, h0, tc0);  // no launch computed layer 0's R for this step
+    }
     for (int l = 0; l < WF_LAYERS; l++) {
         const WfLayerDev& L = net.L[l];
         // stage the same-wavefront weights of the next layer: rows tc_lo .. tc_lo + nrows - 1 are contiguous in wq
@@ -623,6 +653,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                 d = h + __ldg(net.idx + k + HW);
                 tc = sd.psum - d;
                 wf_chain4_prefetch(net, L, n, par, d, h, tc, p);
+                if (l == 0 && r0_inline) p.rr = wf_r_layer0_c1(net, n, d, h, tc);
             }
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             if (L.has_q) {
@@ -955,6 +986,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         e.c1_cmax = 4;
         for (int l = 1; l < WF_LAYERS; l++) { e.chain1 = e.chain1 && (n.L[l].cin_g & 3) == 0; e.c1_cmax = std::max(e.c1_cmax, n.L[l].cin_g); }
         if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = e.chain1 = false;
+        e.r0_inline = e.chain4 && n.L[0].cin_g == 1 && n.L[0].cpg4 == 1 && !getenv("LIC360_WF_R0_KERNEL");
         if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
         if (e.chain1) {
             e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
@@ -1060,7 +1092,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* row
     cfg.attrs = attr;
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
-    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r);
+    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r, (int)(e.r0_inline && r.enabled));
     if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }
