@@ -75,19 +75,20 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, int byt
 //   blockIdx.z -> (layer, net)
 struct WfTile { int l, n, kc, psum, d, hbase, hmax, tc; bool ok; };
 
-__device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp, int l0 = 0) {
+__device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp, int l0 = 0, bool swapped = false) {
     WfTile t;
-    t.l = l0 + blockIdx.z / net.nsets;
-    t.n = blockIdx.z % net.nsets;
+    const int bx = swapped ? blockIdx.z : blockIdx.x, bz = swapped ? blockIdx.x : blockIdx.z;
+    t.l = l0 + bz / net.nsets;
+    t.n = bz % net.nsets;
     t.kc = blockIdx.y;
     t.psum = *net.ctr + dp;
     t.ok = t.kc < net.L[t.l].cpg4 && t.psum < net.nsteps;
     const int la = max(0, t.psum - net.G + 1), lb = min(t.psum, net.H + net.W - 2);
-    t.d = la + blockIdx.x / net.parts;
+    t.d = la + bx / net.parts;
     t.ok = t.ok && t.d <= lb;
     const int hmin = max(0, t.d - net.W + 1);
     t.hmax = min(net.H - 1, t.d);
-    t.hbase = hmin + (blockIdx.x % net.parts) * 32;
+    t.hbase = hmin + (bx % net.parts) * 32;
     t.ok = t.ok && t.hbase <= t.hmax;
     t.tc = t.psum - t.d;
     return t;
@@ -103,7 +104,9 @@ constexpr int WF_OLD_WARPS = 4;  // warps per CTA; warp w walks the canonical bl
 __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_constant__ WfNetDev net,
                                                                   const __grid_constant__ WfMaps maps, int dp) {
     extern __shared__ unsigned char wf_raw[];
-    const WfTile t = wf_tile(net, dp);
+    // grid = ((layer, net), chunk, (diagonal, part)): CTAs are dispatched x-fastest, so the tiles of the LARGEST output
+    // groups (most old terms) of every layer start first and the light ones fill the tail
+    const WfTile t = wf_tile(net, dp, 0, true);
     if (!t.ok) return;  // CTA-uniform
     if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum - dp, WF_TR_OLD0);
     const WfLayerDev& L = net.L[t.l];
@@ -1051,7 +1054,7 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(n.ndiag * n.parts, e.cpg4_max, WF_LAYERS * n.nsets);
+    cfg.gridDim = dim3(WF_LAYERS * n.nsets, e.cpg4_max, n.ndiag * n.parts);
     cfg.blockDim = dim3(32, WF_OLD_WARPS);
     cfg.dynamicSmemBytes = e.old_smem;
     cfg.stream = s;
