@@ -185,7 +185,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
     const float4* w = reinterpret_cast<const float4*>(L.wq) +
                       ((size_t)(cls * net.nsets + n) * L.nchunk + tc * L.cpg4 + kc) * TAPS * cin_g;
     // cell (d-4+kh+kw, group gq, h-2+kh) of the padded frame = xb + (((kh+kw) * GP + gq) * Hp + kh) * cin_g
-    const int Hp = net.Hp, G = net.G, GP = net.G + 2 * WF_GPAD;
+    const int Hp = net.Hp, GP = net.G + 2 * WF_GPAD;
     const float* xb = L.xc + ((((size_t)n * net.Dp + d) * GP + WF_GPAD) * Hp + h) * cin_g;
     (void)C;
     if ((cin_g & 3) == 0 && net.G == 1) {
