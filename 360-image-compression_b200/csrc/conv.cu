@@ -162,6 +162,31 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 #pragma unroll
                         for (int p = 0; p < 4; p++) {
                             float xx = xv[p + kw];
+#ifdef LIC360_FFMA2
+                            asm("{\n"
+                                ".reg .b64 xa, wa, wb, wc, wd, ua, ub, uc, ud;\n"
+                                "mov.b64 xa, {%8, %8};\n"
+                                "mov.b64 wa, {%9, %10};\n"
+                                "mov.b64 wb, {%11, %12};\n"
+                                "mov.b64 wc, {%13, %14};\n"
+                                "mov.b64 wd, {%15, %16};\n"
+                                "mov.b64 ua, {%0, %1};\n"
+                                "mov.b64 ub, {%2, %3};\n"
+                                "mov.b64 uc, {%4, %5};\n"
+                                "mov.b64 ud, {%6, %7};\n"
+                                "fma.rn.f32x2 ua, xa, wa, ua;\n"
+                                "fma.rn.f32x2 ub, xa, wb, ub;\n"
+                                "fma.rn.f32x2 uc, xa, wc, uc;\n"
+                                "fma.rn.f32x2 ud, xa, wd, ud;\n"
+                                "mov.b64 {%0, %1}, ua;\n"
+                                "mov.b64 {%2, %3}, ub;\n"
+                                "mov.b64 {%4, %5}, uc;\n"
+                                "mov.b64 {%6, %7}, ud;\n"
+                                "}\n"
+                                : "+f"(u[0][p][0]), "+f"(u[0][p][1]), "+f"(u[0][p][2]), "+f"(u[0][p][3]), "+f"(u[1][p][0]), "+f"(u[1][p][1]),
+                                  "+f"(u[1][p][2]), "+f"(u[1][p][3])
+                                : "f"(xx), "f"(a4.x), "f"(a4.y), "f"(a4.z), "f"(a4.w), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w));
+#else
                             u[0][p][0] = fmaf(xx, a4.x, u[0][p][0]);
                             u[0][p][1] = fmaf(xx, a4.y, u[0][p][1]);
                             u[0][p][2] = fmaf(xx, a4.z, u[0][p][2]);
@@ -170,6 +195,7 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
                             u[1][p][1] = fmaf(xx, b4.y, u[1][p][1]);
                             u[1][p][2] = fmaf(xx, b4.z, u[1][p][2]);
                             u[1][p][3] = fmaf(xx, b4.w, u[1][p][3]);
+#endif
                         }
                     }
                 }
@@ -273,19 +299,13 @@ __global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq_kernel(const ConvAr
 #pragma unroll
                             for (int c = 0; c < 4; c++) {
                                 const float4 w4 = wt[c];
-                                u.x = fmaf(xx[c], w4.x, u.x);
-                                u.y = fmaf(xx[c], w4.y, u.y);
-                                u.z = fmaf(xx[c], w4.z, u.z);
-                                u.w = fmaf(xx[c], w4.w, u.w);
+                                fma4(u, xx[c], w4);
                             }
                         } else {
                             for (int c = c0; c < c1; c++) {
                                 const float xx = __ldg(xp + (size_t)c * HW);
                                 const float4 w4 = wt[c];
-                                u.x = fmaf(xx, w4.x, u.x);
-                                u.y = fmaf(xx, w4.y, u.y);
-                                u.z = fmaf(xx, w4.z, u.z);
-                                u.w = fmaf(xx, w4.w, u.w);
+                                fma4(u, xx, w4);
                             }
                         }
                     }
@@ -347,19 +367,13 @@ __global__ void __launch_bounds__(640, 2) cconv_ec_rqb_kernel(const ConvArgs a, 
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         const float4 w4 = wt[c0 + c];
-                        u.x = fmaf(xx[c], w4.x, u.x);
-                        u.y = fmaf(xx[c], w4.y, u.y);
-                        u.z = fmaf(xx[c], w4.z, u.z);
-                        u.w = fmaf(xx[c], w4.w, u.w);
+                        fma4(u, xx[c], w4);
                     }
                 } else {
                     for (int c = c0; c < c1; c++) {
                         const float xx = __ldg(xp + (size_t)c * HW);
                         const float4 w4 = wt[c];
-                        u.x = fmaf(xx, w4.x, u.x);
-                        u.y = fmaf(xx, w4.y, u.y);
-                        u.z = fmaf(xx, w4.z, u.z);
-                        u.w = fmaf(xx, w4.w, u.w);
+                        fma4(u, xx, w4);
                     }
                 }
             }

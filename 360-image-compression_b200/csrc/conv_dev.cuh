@@ -103,10 +103,7 @@ __device__ __forceinline__ void dc_stage_q(const float* band, const float4* wsm,
             for (int ch = 0; ch < nc; ch++) {
                 const float xx = band[ch * CHS + (lane + kh) * RS + (kh + kw) * CS];
                 const float4 w4 = wsm[ch * TAPS + kh * 5 + kw];
-                u.x = fmaf(xx, w4.x, u.x);
-                u.y = fmaf(xx, w4.y, u.y);
-                u.z = fmaf(xx, w4.z, u.z);
-                u.w = fmaf(xx, w4.w, u.w);
+                fma4(u, xx, w4);
             }
         }
     }

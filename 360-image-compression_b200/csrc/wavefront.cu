@@ -211,10 +211,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                 const float xs[4] = {xv[kh].x, xv[kh].y, xv[kh].z, xv[kh].w};
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    u.x = fmaf(xs[c], wv[kh][c].x, u.x);
-                    u.y = fmaf(xs[c], wv[kh][c].y, u.y);
-                    u.z = fmaf(xs[c], wv[kh][c].z, u.z);
-                    u.w = fmaf(xs[c], wv[kh][c].w, u.w);
+                    fma4(u, xs[c], wv[kh][c]);
                 }
             }
         }
@@ -243,10 +240,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                     const float xs[4] = {xv[kw].x, xv[kw].y, xv[kw].z, xv[kw].w};
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        u.x = fmaf(xs[c], wv[kw][c].x, u.x);
-                        u.y = fmaf(xs[c], wv[kw][c].y, u.y);
-                        u.z = fmaf(xs[c], wv[kw][c].z, u.z);
-                        u.w = fmaf(xs[c], wv[kw][c].w, u.w);
+                        fma4(u, xs[c], wv[kw][c]);
                     }
                 }
             }
@@ -265,10 +259,7 @@ __device__ __forceinline__ float4 wf_rq_partial(const WfNetDev& net, const WfLay
                     for (int c = 0; c < nc; c++) {
                         const float xx = CG ? __ldcg(xp + c) : __ldg(xp + c);
                         const float4 w4 = __ldg(wt + c);
-                        u.x = fmaf(xx, w4.x, u.x);
-                        u.y = fmaf(xx, w4.y, u.y);
-                        u.z = fmaf(xx, w4.z, u.z);
-                        u.w = fmaf(xx, w4.w, u.w);
+                        fma4(u, xx, w4);
                     }
                 }
             }
@@ -333,7 +324,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         const float4 w4 = wt[c];
-                        u.x = fmaf(xs[c], w4.x, u.x); u.y = fmaf(xs[c], w4.y, u.y); u.z = fmaf(xs[c], w4.z, u.z); u.w = fmaf(xs[c], w4.w, u.w);
+                        fma4(u, xs[c], w4);
                     }
                 }
             }
@@ -361,7 +352,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
                             const float4 w4 = wt[c];
-                            u.x = fmaf(xs[c], w4.x, u.x); u.y = fmaf(xs[c], w4.y, u.y); u.z = fmaf(xs[c], w4.z, u.z); u.w = fmaf(xs[c], w4.w, u.w);
+                            fma4(u, xs[c], w4);
                         }
                     }
             }
@@ -379,7 +370,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
                         for (int c = 0; c < nc; c++) {
                             const float xx = __ldg(xp + c);
                             const float4 w4 = wt[c];
-                            u.x = fmaf(xx, w4.x, u.x); u.y = fmaf(xx, w4.y, u.y); u.z = fmaf(xx, w4.z, u.z); u.w = fmaf(xx, w4.w, u.w);
+                            fma4(u, xx, w4);
                         }
                     }
             }
@@ -538,7 +529,7 @@ __device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d,
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < TAPS; t++) {
-        u.x = fmaf(xv[t], wv[t].x, u.x); u.y = fmaf(xv[t], wv[t].y, u.y); u.z = fmaf(xv[t], wv[t].z, u.z); u.w = fmaf(xv[t], wv[t].w, u.w);
+        fma4(u, xv[t], wv[t]);
     }
     return make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0 (one canonical block)
 }
@@ -680,10 +671,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
                             const float4 w4 = wr[(kh * 5 + kw) * 4 + c];
-                            u.x = fmaf(xs[c], w4.x, u.x);
-                            u.y = fmaf(xs[c], w4.y, u.y);
-                            u.z = fmaf(xs[c], w4.z, u.z);
-                            u.w = fmaf(xs[c], w4.w, u.w);
+                            fma4(u, xs[c], w4);
                         }
                     }
             }
@@ -813,10 +801,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
 #pragma unroll
                             for (int c = 0; c < 4; c++) {
                                 const float4 w4 = wr[c];
-                                u.x = fmaf(x4[c], w4.x, u.x);
-                                u.y = fmaf(x4[c], w4.y, u.y);
-                                u.z = fmaf(x4[c], w4.z, u.z);
-                                u.w = fmaf(x4[c], w4.w, u.w);
+                                fma4(u, x4[c], w4);
                             }
                         }
                     }
