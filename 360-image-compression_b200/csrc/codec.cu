@@ -56,6 +56,7 @@ struct NetDesc {
     int* done_dev = nullptr;            // CTA counter of the rows kernel
     int* sync_dev = nullptr;            // code stream: monotone cross-cluster counter of the chain kernel's rows phase
     int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
+    int* go_host = nullptr;             // mapped pinned: the stream may run step p once this is >= p (launch-ahead, decode_stream)
     uint16_t* rows_dev = nullptr;       // encode: all rows of the stream
     uint16_t* rows_host = nullptr;      // pinned
     uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
@@ -84,7 +85,10 @@ struct lic360_codec {
 namespace lic360 {
 
 WF_TRACE_DECL
-static void codec_trace_set(unsigned long long* buf) { cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf)); }
+static void codec_trace_set(unsigned long long* buf, int sel) {
+    cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_wf_trace_sel, &sel, sizeof(sel));
+}
 
 // ------------------------------------------------------------------------------------------------ kernels
 // code stream encoder input: x = (code - 3.5) * mask replicated for the 3 nets (lic360_demo.py:130-131)
@@ -174,7 +178,7 @@ __global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __res
                                     int G, int H, int W, int D, int HS, int Dp, int Hp, float bias, float scale, int rep,
                                     float* __restrict__ keep) {
     const int c = *ctr;
-    if (G > 1 && threadIdx.x == 0) WF_TRACE_MIN(c, WF_TR_SCATTER);
+    if (threadIdx.x == 0 && blockIdx.x == 0) WF_TRACE_MIN(G, c, WF_TR_SCATTER);
     if (c == 0) return;
     const StepDesc d = steps[c - 1];
     const int HW = H * W;
@@ -204,7 +208,7 @@ __global__ void finish_code_kernel(const float* __restrict__ fc0, const float* _
 }
 
 // all rows of a step are in mapped pinned memory: the last CTA raises the host flag
-__device__ __forceinline__ void rows_done(int* done, volatile int* flag, int step) {
+__device__ __forceinline__ void rows_done(int* done, volatile int* flag, int step, int G) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -212,7 +216,7 @@ __device__ __forceinline__ void rows_done(int* done, volatile int* flag, int ste
             *done = 0;
             __threadfence_system();
             *flag = step + 1;
-            if (gridDim.x > 4) WF_TRACE_MAX(step, WF_TR_ROWS1);
+            WF_TRACE_MAX(G, step, WF_TR_ROWS1);
         }
     }
 }
@@ -227,7 +231,7 @@ __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __r
                                    const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
                                    int G, int H, int W, int Dp, int Hp, float s2, int* done, int* flag) {
     const int step = *ctr;
-    if (threadIdx.x == 0) WF_TRACE_MIN(step, WF_TR_ROWS0);
+    if (threadIdx.x == 0) WF_TRACE_MIN(G, step, WF_TR_ROWS0);
     const StepDesc d = steps[step];
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = gt >> 3, j = gt & 7;
@@ -257,35 +261,30 @@ __global__ void gmm_rows_wf_kernel(const float* __restrict__ y, const float* __r
         const int lvl = (int)(levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
         pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows + (size_t)l * 8);
     }
-    rows_done(done, flag, step);
+    rows_done(done, flag, step, G);
 }
 
-__device__ __forceinline__ void pack_imp_row(const float* o, int sym, uint16_t* dst) {
-    uint32_t ovf[3] = {0, 0, 0};
-    for (int j = 1; j <= 48; j++) {
-        const uint32_t v = (uint32_t)(int)o[j];
-        dst[j - 1] = (uint16_t)(v & 0xFFFF);
-        ovf[(j - 1) / 16] |= ((v >> 16) & 1u) << ((j - 1) % 16);
-    }
-    dst[48] = (uint16_t)sym;
-    dst[49] = (uint16_t)ovf[0]; dst[50] = (uint16_t)ovf[1]; dst[51] = (uint16_t)ovf[2];
-}
-
-__global__ void imp_rows_wf_kernel(const float* __restrict__ y, const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps,
-                                   const int* __restrict__ ctr, uint16_t* __restrict__ rows, int H, int W, int Dp, int Hp, int* done,
-                                   int* flag) {
+// decoder, importance stream: CDF row of every position of the step's diagonal from the 49 logits of the engine's last frame.
+// One WARP per symbol (the step has <= min(H, W) symbols and sits on the critical path of BOTH streams, so it is latency that
+// counts): lanes hold logits i and i + 32, the softmax denominator is accumulated in index order by every lane from shared memory
+// (the serial order of entropy_row, tables_dev.cuh, is part of the bit-exact contract), the cumulative table is a warp scan of
+// integers (exact in fp32, so min(prefix, total) equals the serial clipped recurrence), lane 0 runs the serial fix-up and the
+// warp stores the packed 128-byte row with one coalesced write.
+constexpr int IMP_ROWS_WARPS = 8;
+__global__ void __launch_bounds__(32 * IMP_ROWS_WARPS) imp_rows_wf_kernel(const float* __restrict__ y, const int32_t* __restrict__ idx,
+                                   const StepDesc* __restrict__ steps, const int* __restrict__ ctr, uint16_t* __restrict__ rows,
+                                   int H, int W, int Dp, int Hp, int* done, int* flag) {
+    __shared__ float sh[IMP_ROWS_WARPS][64];
     const int step = *ctr;
+    if (threadIdx.x == 0) WF_TRACE_MIN(1, step, WF_TR_ROWS0);
     const StepDesc d = steps[step];
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l < d.len) {
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int l = blockIdx.x * IMP_ROWS_WARPS + wp; l < d.len; l += gridDim.x * IMP_ROWS_WARPS) {  // warp-uniform
         const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + H * W);
-        float o[50];
         const float* yp = y + wf_fc_index(Dp, Hp, 1, 49, 0, th + tw, 0, th);
-        for (int i = 0; i < 49; i++) o[1 + i] = yp[i];
-        entropy_row(o, 49, 65536.f);
-        pack_imp_row(o, 0, rows + (size_t)l * 64);
+        entropy_row49_warp(yp[lane], lane + 32 < 49 ? yp[lane + 32] : -INFINITY, sh[wp], lane, 0, rows + (size_t)l * 64);
     }
-    rows_done(done, flag, step);
+    rows_done(done, flag, step, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers
@@ -400,7 +399,7 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("scatter kernel");
     const bool fork = side != s;  // graph capture: overlap the old terms of the next step with the chain (see below)
     if (ev) LIC360_CUDA(cudaEventRecord(ev[1], s));
-    const bool fused_rows = is_code && n.wf.chain4 && !getenv("LIC360_WF_ROWS_KERNEL");
+    const bool fused_rows = (is_code ? n.wf.chain4 : n.wf.chain1) && !getenv("LIC360_WF_ROWS_KERNEL");
     if (!(fused_rows && n.wf.r0_inline)) {  // else the chain kernel evaluates them in its prologue
         LIC360_CUDA(wf_launch_prev(n.wf, 0, 0, 1, s));  // layer 0 only: its taps read the symbols scattered a moment ago
         WF_DEBUG_SYNC("previous-wavefront kernel (layer 0)");
@@ -413,11 +412,17 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
         rows.rows = n.rows_step_host; rows.levels = c->levels_dev; rows.done = n.done_dev; rows.flag = n.flag_host;
         rows.sync = n.sync_dev; rows.s2 = (float)(1. / sqrt(2.0)); rows.enabled = 1;
     }
+    // code stream: the chain kernel also leaves the previous-wavefront terms of the next step behind (no launch, no side branch)
+    const bool rtail = fused_rows && is_code && n.wf.chain4 && !getenv("LIC360_WF_PREV_KERNEL");
+    rows.rtail = rtail ? 1 : 0;
     LIC360_CUDA(wf_launch_chain(n.wf, s, fused_rows ? &rows : nullptr));
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
     cudaStream_t rs = s;  // stream of the rows kernel
-    if (fork) {
+    if (fork && rtail) {
+        LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
+        LIC360_CUDA(wf_launch_old(n.wf, 1, s, true));  // programmatic dependent of the chain kernel, see below
+    } else if (fork) {
         // The old terms of step p+1 only read wavefronts <= p-1: they are launched right behind the chain kernel as its
         // PROGRAMMATIC dependent -- they start once every chain CTA is resident (so the chain's clusters got their SMs
         // first) and fill the SMs the chain leaves idle.  The rows kernel needs the chain's RESULTS, so it waits for the
@@ -433,16 +438,19 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
                                                  n.steps_dev, n.ctr_dev, n.rows_step_host, n.G, n.H, n.W, w.Dp, w.Hp,
                                                  (float)(1. / sqrt(2.0)), n.done_dev, n.flag_host);
     else
-        imp_rows_wf_kernel<<<tgrid, 128, 0, rs>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
+        imp_rows_wf_kernel<<<std::max(1, std::min(4, (n.max_len + IMP_ROWS_WARPS - 1) / IMP_ROWS_WARPS)), 32 * IMP_ROWS_WARPS, 0, rs>>>(n.wf.fc[12], n.idx_dev, n.steps_dev, n.ctr_dev, n.rows_step_host, n.H, n.W, w.Dp, w.Hp,
                                                  n.done_dev, n.flag_host);
     if (!fused_rows) LAUNCH_CHECK();
     WF_DEBUG_SYNC("rows kernel");
     // previous-wavefront terms of layers 1..11 for step p+1 (the activations of wavefront p are final): behind the rows
     // kernel, i.e. underneath the host decoder instead of on the critical path
-    LIC360_CUDA(wf_launch_prev(n.wf, 1, 1, WF_LAYERS, rs));
+    if (!rtail) LIC360_CUDA(wf_launch_prev(n.wf, 1, 1, WF_LAYERS, rs));
     WF_DEBUG_SYNC("previous-wavefront kernel (layers 1..11 of the next step)");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
-    if (fork) {
+    if (fork && rtail) {
+        // the old-term kernel is only a PROGRAMMATIC dependent of the chain: make the step counter wait for the chain itself too
+        LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_fork, 0));
+    } else if (fork) {
         LIC360_CUDA(cudaEventRecord(n.ev_join, side));
         LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_join, 0));
     } else {
@@ -514,6 +522,8 @@ static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int pri
     LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.sync_dev, sizeof(int)));
     LIC360_CUDA(cudaHostAlloc(&n.flag_host, sizeof(int), cudaHostAllocMapped));
+    LIC360_CUDA(cudaHostAlloc(&n.go_host, 64, cudaHostAllocMapped));
+    *n.go_host = 0;
     n.coder = lic360_coder_create("", fill);
     return n.coder ? LIC360_OK : LIC360_ERR_ARG;
 }
@@ -527,7 +537,7 @@ static int ctx_buffers(NetDesc& n) {
 }
 
 static void ctx_free(NetDesc& n) {
-    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host);
+    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host); cudaFreeHost(n.go_host);
     cudaFree(n.rows_dev); cudaFreeHost(n.rows_host); cudaFreeHost(n.rows_step_host); cudaFreeHost(n.syms_host);
     if (n.ev_fork) cudaEventDestroy(n.ev_fork);
     if (n.ev_join) cudaEventDestroy(n.ev_join);
@@ -678,6 +688,30 @@ long lic360_codec_stream_copy(lic360_codec* c, int stream_id, uint8_t* out, long
     return lic360_coder_get_bytes(stream_id ? c->imp.coder : c->code.coder, out, cap);
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_value_fn() {
+    static StreamWaitValue32Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("LIC360_WF_LAUNCH_AHEAD") &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<StreamWaitValue32Fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// releases a stream that may be parked on its go flag, whatever way decode_stream is left (a parked stream never drains)
+struct GoRelease {
+    int* go;
+    ~GoRelease() { __atomic_store_n(go, 0x7fffffff, __ATOMIC_RELEASE); }
+};
+
 // wait for the rows of step p without synchronising the stream (a later kernel of the step graph may still be running)
 static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
     volatile int* f = n.flag_host;
@@ -724,6 +758,20 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaStream_t s = n.stream;
     int rc = LIC360_OK;
     *n.flag_host = 0;
+    // Launch-ahead (experiment, LIC360_WF_LAUNCH_AHEAD=1; measured ~1 ms SLOWER per 512x1024 decode than launching each step's
+    // graph when its symbols are ready, so it is off by default): while the GPU works on step p the host already enqueues
+    // [wait until *go >= p+1][graph of step p+1]; once the symbols of step p are decoded (and, for the code stream, the importance
+    // levels step p+1 needs are there) one store to the mapped flag lets the stream's front end start the step.  The wait is a
+    // stream memory operation (no kernel spins); GoRelease un-parks the stream on every exit path.
+    StreamWaitValue32Fn wait_value = c->mode == 0 ? stream_wait_value_fn() : nullptr;
+    CUdeviceptr go_dev = 0;
+    if (wait_value) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, n.go_host, 0) != cudaSuccess) { cudaGetLastError(); wait_value = nullptr; }
+        go_dev = (CUdeviceptr)(uintptr_t)dp;
+    }
+    __atomic_store_n(n.go_host, 0, __ATOMIC_RELEASE);
+    GoRelease go_release{n.go_host};
     n.t_host_coder = 0; n.t_gpu_wait = 0;
     LIC360_CUDA(wf_clear(n.wf, s));
     LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0, sizeof(int), s));
@@ -732,27 +780,44 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     LIC360_CUDA(wf_launch_old(n.wf, 0, s));  // old terms of step 0 (all zero, but it keeps the schedule uniform)
     if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
+    auto wait_levels = [&](int p) -> int {  // code stream: the importance levels step p needs are decoded
+        const int need = std::min(p, n.H + n.W - 2) / 2 + 1;
+        const auto t0 = clk::now();
+        for (unsigned spins = 1; c->imp_ready.load(std::memory_order_acquire) < need; spins++) {
+            if ((spins & 0xFFF) == 0 && (c->abort_flag.load() || ms_since(t0) > 20000.)) {
+                set_error("codec: the importance stream did not deliver the levels the code stream needs");
+                return LIC360_ERR_CODER;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0x1F) == 0) sched_yield();
+        }
+        return LIC360_OK;
+    };
+    bool ahead = false;  // the graph of the current step is already enqueued (behind its go flag)
     for (int p = 0; p < n.nsteps; p++) {
         auto tw = clk::now();
-        if (is_code) {
-            const int need = std::min(p, n.H + n.W - 2) / 2 + 1;
-            for (unsigned spins = 1; c->imp_ready.load(std::memory_order_acquire) < need; spins++) {
-                if ((spins & 0xFFF) == 0 && (c->abort_flag.load() || ms_since(tw) > 20000.)) {
-                    set_error("codec: the importance stream did not deliver the levels the code stream needs");
-                    return LIC360_ERR_CODER;
-                }
-#if defined(__x86_64__)
-                __builtin_ia32_pause();
-#endif
-                if ((spins & 0x1F) == 0) sched_yield();
-            }
-        }
         if (c->mode == 0) {
-            LIC360_CUDA(cudaGraphLaunch(n.graph, s));
-            g_launches += n.graph_nodes;
+            if (!ahead) {
+                if (is_code) { rc = wait_levels(p); if (rc) return rc; }
+                LIC360_CUDA(cudaGraphLaunch(n.graph, s));
+                g_launches += n.graph_nodes;
+            }
+            ahead = false;
+            if (wait_value && p + 1 < n.nsteps) {
+                if (wait_value(s, go_dev, (cuuint32_t)(p + 1), 0 /* CU_STREAM_WAIT_VALUE_GEQ */) == CUDA_SUCCESS) {
+                    LIC360_CUDA(cudaGraphLaunch(n.graph, s));
+                    g_launches += n.graph_nodes;
+                    ahead = true;
+                } else {
+                    wait_value = nullptr;  // not supported here: plain launch per step
+                }
+            }
             rc = wait_rows(c, n, p);
             if (rc) return rc;
         } else {
+            if (is_code) { rc = wait_levels(p); if (rc) return rc; }
             rc = launch_step(c, n, is_code, s, s, n.ev_prof);
             if (rc) return rc;
             LIC360_CUDA(cudaStreamSynchronize(s));
@@ -768,6 +833,10 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
                      : coder_decode_packed_imp(n.coder, n.rows_step_host, len, n.syms_host);
         n.t_host_coder += ms_since(th);
         if (rc) return rc;
+        if (ahead) {
+            if (is_code) { rc = wait_levels(p + 1); if (rc) return rc; }
+            __atomic_store_n(n.go_host, p + 1, __ATOMIC_RELEASE);  // symbols of step p are in syms_host: step p+1 may run
+        }
     }
     rc = final_scatter(c, n, is_code);
     if (rc) return rc;
@@ -791,16 +860,18 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     c->abort_flag.store(0);
     // debug timeline of the code stream (LIC360_WF_TRACE=1): %globaltimer stamps per step, summarised on stderr
     unsigned long long* trace_dev = nullptr;
-    const int tr_steps = c->code.nsteps + 2;
+    const int tr_sel = getenv("LIC360_WF_TRACE") && atoi(getenv("LIC360_WF_TRACE")) == 2 ? 1 : 0;  // 2: trace the importance stream
+    const NetDesc& tr_net = tr_sel ? c->imp : c->code;
+    const int tr_steps = tr_net.nsteps + 2;
     if (getenv("LIC360_WF_TRACE")) {
-        std::vector<unsigned long long> init((size_t)tr_steps * WF_TR_SLOTS);
+        std::vector<unsigned long long> init((size_t)tr_steps * WF_TR_SLOTS + 64, 0ull);  // + per-layer phase sums of the G = 1 chain
         for (int p = 0; p < tr_steps; p++)
             for (int k = 0; k < WF_TR_SLOTS; k++)
                 init[(size_t)p * WF_TR_SLOTS + k] = (k == WF_TR_CHAIN1 || k == WF_TR_ROWS1 || k == WF_TR_OLD1) ? 0ull : ~0ull;
         LIC360_CUDA(cudaMalloc(&trace_dev, init.size() * 8));
         LIC360_CUDA(cudaMemcpy(trace_dev, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
-        wf_trace_set(trace_dev);
-        codec_trace_set(trace_dev);
+        wf_trace_set(trace_dev, tr_sel);
+        codec_trace_set(trace_dev, tr_sel);
     }
     if (c->mode == 0) {  // both step graphs exist before the second host thread starts
         rc = build_step_graph(c, c->imp, false);
@@ -845,24 +916,32 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
     LAUNCH_CHECK();
     LIC360_CUDA(cudaStreamSynchronize(s));
     if (trace_dev) {
-        std::vector<unsigned long long> tr((size_t)tr_steps * WF_TR_SLOTS);
+        std::vector<unsigned long long> tr((size_t)tr_steps * WF_TR_SLOTS + 64);
         cudaMemcpy(tr.data(), trace_dev, tr.size() * 8, cudaMemcpyDeviceToHost);
-        wf_trace_set(nullptr);
-        codec_trace_set(nullptr);
+        wf_trace_set(nullptr, 0);
+        codec_trace_set(nullptr, 0);
         cudaFree(trace_dev);
         const char* names[WF_TR_SLOTS] = {"scatter start", "prev start", "chain start", "chain end", "rows start", "rows flag", "old start", "old end"};
         for (int w0 = 0; w0 < 2; w0++) {  // two windows: while the importance stream still runs / after it finished
-            const int pa = w0 == 0 ? 20 : 140, pb = w0 == 0 ? 80 : 220;
+            const int pa = tr_sel ? (w0 == 0 ? 10 : 50) : (w0 == 0 ? 20 : 140), pb = tr_sel ? (w0 == 0 ? 45 : 90) : (w0 == 0 ? 80 : 220);
             double acc[WF_TR_SLOTS] = {0}, period = 0;
             int cnt = 0;
-            for (int p = pa; p < pb && p + 1 < c->code.nsteps; p++) {
+            for (int p = pa; p < pb && p + 1 < tr_net.nsteps; p++) {
                 const unsigned long long* r = &tr[(size_t)p * WF_TR_SLOTS];
                 for (int k = 0; k < WF_TR_SLOTS; k++) acc[k] += (double)(long long)(r[k] - r[0]) * 1e-3;
                 period += (double)(long long)(tr[(size_t)(p + 1) * WF_TR_SLOTS] - r[0]) * 1e-3;
                 cnt++;
             }
-            fprintf(stderr, "lic360 trace, code-stream steps %d..%d: period %.1f us;", pa, pb, period / cnt);
+            fprintf(stderr, "lic360 trace, %s-stream steps %d..%d: period %.1f us;", tr_sel ? "importance" : "code", pa, pb, period / cnt);
             for (int k = 1; k < WF_TR_SLOTS; k++) fprintf(stderr, " %s +%.1f;", names[k], acc[k] / cnt);
+            fprintf(stderr, "\n");
+        }
+        if (tr_sel) {
+            fprintf(stderr, "lic360 trace, G=1 chain, CTA 0, us per layer [weight staging | Q product | epilogue + DSMEM stores | prefetch + cluster barrier]:");
+            for (int l = 0; l < 12; l++) {
+                fprintf(stderr, " L%d", l);
+                for (int ph = 0; ph < 4; ph++) fprintf(stderr, "%c%.2f", ph ? '|' : ' ', (double)tr[(size_t)tr_steps * WF_TR_SLOTS + l * 4 + ph] * 1e-3 / tr_net.nsteps);
+            }
             fprintf(stderr, "\n");
         }
     }

@@ -157,24 +157,66 @@ int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows) {
     return LIC360_OK;
 }
 
+// Decoder state kept in locals for a whole slab; `code` is refilled through the 64-bit accumulator of the bit reader.
+// The symbol search is division-free: with value = floor(num / range), num = ((code - low + 1) << 16) - 1,
+//     T[j] <= value  <=>  T[j] * range <= num          (T[j] integer, range > 0)
+// so the symbol is the number of interior bins whose 48-bit product does not exceed num (the rows are strictly increasing after the
+// fix-up, the same symbol the reference's binary search ArithmeticCoder.cpp:92-116 returns), the seven products are independent
+// (no 64-bit divide, no data-dependent branch) and the two the range update needs (ArithmeticCoder.cpp:50-53) are among them.
+struct DecState {
+    uint32_t low, high, code;
+    BitReader* br;
+    inline bool update(uint64_t pl, uint64_t ph) {  // pl, ph = T[s] * range, T[s+1] * range; total = 65536
+        uint32_t lo = low + (uint32_t)(pl >> 16), hi = low + (uint32_t)(ph >> 16) - 1;
+        const uint32_t diff = lo ^ hi;
+        if (pl == ph || diff == 0) return false;
+        const int n = __builtin_clz(diff);
+        if (n > 0) {
+            code = (code << n) | br->get(n);
+            lo <<= n;
+            hi = (hi << n) | ((1u << n) - 1);
+        }
+        const uint32_t m = (lo & ~hi) << 1;
+        const int k = __builtin_clz(~m | 1u);
+        if (k > 0) {
+            code = (code & 0x80000000u) | ((code << k) & 0x7FFFFFFFu) | br->get(k);
+            lo = (lo << k) & 0x7FFFFFFFu;
+            hi = ((hi << k) & 0x7FFFFFFFu) | 0x80000000u | ((1u << k) - 1);
+        }
+        low = lo; high = hi;
+        return code >= lo && code <= hi;
+    }
+};
+
 int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, float* out) {
+    DecState st{(uint32_t)c->low, (uint32_t)c->high, (uint32_t)c->code, &c->br};
+    const float fill = c->fill;
+    int rc = LIC360_OK;
     for (int i = 0; i < nrows; i++) {
         const uint16_t* r = rows + (size_t)i * 8;
-        if (!((r[7] >> 8) & 1)) { out[i] = c->fill; continue; }  // coder.cpp:101-102
-        const uint64_t range = c->high - c->low + 1;
-        const uint64_t offset = c->code - c->low;
-        const uint64_t value = (((offset + 1) << 16) - 1) / range;
-        uint32_t s = 0, e = 8;
-        while (e - s > 1) {
-            const uint32_t mid = (s + e) >> 1;
-            if (gmm_bin(r, mid) > value) e = mid; else s = mid;
+        const uint32_t meta = r[7];
+        if (!((meta >> 8) & 1)) { out[i] = fill; continue; }  // coder.cpp:101-102
+        const uint64_t range = (uint64_t)st.high - st.low + 1;
+        const uint64_t num = (((uint64_t)(st.code - st.low) + 1) << 16) - 1;
+        uint64_t prod[9];
+        prod[0] = 0;
+        prod[8] = range << 16;
+        uint32_t s = 0;
+#pragma GCC unroll 7
+        for (int j = 1; j <= 7; j++) {
+            const uint64_t t = (uint64_t)r[j - 1] | ((uint64_t)((meta >> (9 + j - 1)) & 1u) << 16);
+            prod[j] = t * range;
+            s += prod[j] <= num;
         }
-        int rc = ac_update<true>(c, gmm_bin(r, s), gmm_bin(r, s + 1), 65536);
-        if (rc) return rc;
-        if (c->code < c->low || c->code > c->high) { set_error("coder: code out of range (corrupt stream or table mismatch)"); return LIC360_ERR_CODER; }
+        if (!st.update(prod[s], prod[s + 1])) {
+            set_error("coder: corrupt stream or table mismatch (zero-frequency symbol or code out of range)");
+            rc = LIC360_ERR_CODER;
+            break;
+        }
         out[i] = (float)s;
     }
-    return LIC360_OK;
+    c->low = st.low; c->high = st.high; c->code = st.code;
+    return rc;
 }
 
 static inline uint32_t imp_bin(const uint16_t* r, int j) {  // j in 0..49
@@ -218,6 +260,18 @@ const uint8_t* coder_bytes(lic360_coder* c, long* n) { *n = (long)c->bw.bytes.si
 }  // namespace lic360
 
 extern "C" {
+
+int lic360_coder_encode_rows(lic360_coder* c, const uint16_t* rows, int nrows, int kind) {
+    if (!c || !rows || nrows < 0 || (kind != 0 && kind != 1)) { lic360::set_error("coder: bad arguments"); return LIC360_ERR_ARG; }
+    if (!c->encoding) { lic360::set_error("coder: encode without start_encoder"); return LIC360_ERR_CODER; }
+    return kind == 0 ? lic360::coder_encode_packed_gmm(c, rows, nrows) : lic360::coder_encode_packed_imp(c, rows, nrows);
+}
+
+int lic360_coder_decode_rows(lic360_coder* c, const uint16_t* rows, int nrows, int kind, float* out) {
+    if (!c || !rows || !out || nrows < 0 || (kind != 0 && kind != 1)) { lic360::set_error("coder: bad arguments"); return LIC360_ERR_ARG; }
+    if (!c->decoding) { lic360::set_error("coder: decode without start_decoder"); return LIC360_ERR_CODER; }
+    return kind == 0 ? lic360::coder_decode_packed_gmm(c, rows, nrows, out) : lic360::coder_decode_packed_imp(c, rows, nrows, out);
+}
 
 lic360_coder* lic360_coder_create(const char* fname, float fill_value) {
     lic360_coder* c = new lic360_coder();

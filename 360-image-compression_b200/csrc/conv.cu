@@ -86,6 +86,29 @@ __global__ void cconv_pack_kernel(const float* __restrict__ w, float* __restrict
 // blocks staged in shared memory (x tile with halo + masked weight tile), 25 taps unrolled.
 // ---------------------------------------------------------------------------------------------------------
 
+// one input channel of the EC thread tile (4 positions along w x 2 chunks x 4 channels): taps with kh + kw < NS, fully unrolled
+// with compile-time tap tests; x row = two float4 (8 consecutive columns), weights broadcast from shared memory
+template <int NS>
+__device__ __forceinline__ void ec_taps_fma(const float* xr, const float4* wA, const float4* wB, float4 (&u)[2][4]) {
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++) {
+        if (kh >= NS) continue;
+        const float4 x0 = *reinterpret_cast<const float4*>(xr + kh * XW);
+        const float4 x1 = *reinterpret_cast<const float4*>(xr + kh * XW + 4);
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            if (kh + kw >= NS) continue;
+            const float4 a4 = wA[kh * 5 + kw], b4 = wB[kh * 5 + kw];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                fma4(u[0][p], xv[p + kw], a4);
+                fma4(u[1][p], xv[p + kw], b4);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a) {
     extern __shared__ float4 smem_f4[];
     float* xs = reinterpret_cast<float*>(smem_f4);  // [CB][XH][XW]
@@ -133,13 +156,11 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
         }
         __syncthreads();
         if (j * CB < my_lim) {  // warp-uniform: tz is constant inside a warp
-            float u[2][4][4];
+            float4 u[2][4];
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) u[c][p][q] = 0.f;
+                for (int p = 0; p < 4; p++) u[c][p] = make_float4(0.f, 0.f, 0.f, 0.f);
             // old taps of input group g for output group g_out: kh + kw <= g_out + 2 - g; beyond smax both chunks of
             // this thread carry zero weights (warp-uniform skip; a single-group net keeps 6 of its 25 taps)
             const int gmax_out = min(cA + 1, a.nchunk - 1) / a.cpg4;
@@ -147,65 +168,30 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
             for (int ci = 0; ci < cb; ci++) {
                 const float4* wA = ws4 + ((2 * tz) * CB + ci) * TAPS;
                 const float4* wB = ws4 + ((2 * tz + 1) * CB + ci) * TAPS;
-                const int smax = gmax_out + 2 - (j * CB + ci) / a.cin_g;
-#pragma unroll
-                for (int kh = 0; kh < 5; kh++) {
-                    if (kh > smax) break;
-                    const float* xr = xs + (ci * XH + ty + kh) * XW + 4 * tx;
-                    float4 x0 = *reinterpret_cast<const float4*>(xr);
-                    float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
-                    float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                    for (int kw = 0; kw < 5; kw++) {
-                        if (kh + kw > smax) break;
-                        float4 a4 = wA[kh * 5 + kw], b4 = wB[kh * 5 + kw];
-#pragma unroll
-                        for (int p = 0; p < 4; p++) {
-                            float xx = xv[p + kw];
-#ifdef LIC360_FFMA2
-                            asm("{\n"
-                                ".reg .b64 xa, wa, wb, wc, wd, ua, ub, uc, ud;\n"
-                                "mov.b64 xa, {%8, %8};\n"
-                                "mov.b64 wa, {%9, %10};\n"
-                                "mov.b64 wb, {%11, %12};\n"
-                                "mov.b64 wc, {%13, %14};\n"
-                                "mov.b64 wd, {%15, %16};\n"
-                                "mov.b64 ua, {%0, %1};\n"
-                                "mov.b64 ub, {%2, %3};\n"
-                                "mov.b64 uc, {%4, %5};\n"
-                                "mov.b64 ud, {%6, %7};\n"
-                                "fma.rn.f32x2 ua, xa, wa, ua;\n"
-                                "fma.rn.f32x2 ub, xa, wb, ub;\n"
-                                "fma.rn.f32x2 uc, xa, wc, uc;\n"
-                                "fma.rn.f32x2 ud, xa, wd, ud;\n"
-                                "mov.b64 {%0, %1}, ua;\n"
-                                "mov.b64 {%2, %3}, ub;\n"
-                                "mov.b64 {%4, %5}, uc;\n"
-                                "mov.b64 {%6, %7}, ud;\n"
-                                "}\n"
-                                : "+f"(u[0][p][0]), "+f"(u[0][p][1]), "+f"(u[0][p][2]), "+f"(u[0][p][3]), "+f"(u[1][p][0]), "+f"(u[1][p][1]),
-                                  "+f"(u[1][p][2]), "+f"(u[1][p][3])
-                                : "f"(xx), "f"(a4.x), "f"(a4.y), "f"(a4.z), "f"(a4.w), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w));
-#else
-                            u[0][p][0] = fmaf(xx, a4.x, u[0][p][0]);
-                            u[0][p][1] = fmaf(xx, a4.y, u[0][p][1]);
-                            u[0][p][2] = fmaf(xx, a4.z, u[0][p][2]);
-                            u[0][p][3] = fmaf(xx, a4.w, u[0][p][3]);
-                            u[1][p][0] = fmaf(xx, b4.x, u[1][p][0]);
-                            u[1][p][1] = fmaf(xx, b4.y, u[1][p][1]);
-                            u[1][p][2] = fmaf(xx, b4.z, u[1][p][2]);
-                            u[1][p][3] = fmaf(xx, b4.w, u[1][p][3]);
-#endif
-                        }
-                    }
+                const float* xr = xs + (ci * XH + ty) * XW + 4 * tx;
+                const int ns = gmax_out + 3 - (j * CB + ci) / a.cin_g;  // taps with kh + kw < ns (warp-uniform)
+                if (ns >= 9) { ec_taps_fma<9>(xr, wA, wB, u); continue; }  // the common case: straight-line, no tap tests
+                switch (ns) {
+                    case 8: ec_taps_fma<8>(xr, wA, wB, u); break;
+                    case 7: ec_taps_fma<7>(xr, wA, wB, u); break;
+                    case 6: ec_taps_fma<6>(xr, wA, wB, u); break;
+                    case 5: ec_taps_fma<5>(xr, wA, wB, u); break;
+                    case 4: ec_taps_fma<4>(xr, wA, wB, u); break;
+                    case 3: ec_taps_fma<3>(xr, wA, wB, u); break;
+                    case 2: ec_taps_fma<2>(xr, wA, wB, u); break;
+                    case 1: ec_taps_fma<1>(xr, wA, wB, u); break;
+                    default: break;
                 }
             }
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
-                for (int p = 0; p < 4; p++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) P[c][p][q] = P[c][p][q] + u[c][p][q];
+                for (int p = 0; p < 4; p++) {
+                    P[c][p][0] = P[c][p][0] + u[c][p].x;
+                    P[c][p][1] = P[c][p][1] + u[c][p].y;
+                    P[c][p][2] = P[c][p][2] + u[c][p].z;
+                    P[c][p][3] = P[c][p][3] + u[c][p].w;
+                }
         }
         __syncthreads();
     }

@@ -77,6 +77,63 @@ __device__ __forceinline__ void entropy_row(float* o, int w, float total) {
     fixup_row(o, w, false);
 }
 
+
+// EntropyTable row of 49 logits by ONE WARP (the importance stream's rows sit on the critical path of the decoder: latency counts).
+// Lanes hold logits i and i + 32 (v1 = -inf for i + 32 >= 49); the softmax denominator is accumulated in index order by every lane
+// from shared memory (the serial order of entropy_row is part of the bit-exact contract), the cumulative table is a warp scan of
+// integers (exact in fp32, so min(prefix, total) equals the serial clipped recurrence), lane 0 runs the serial fix-up and the warp
+// stores the packed 128-byte row (coder_internal.h) with one coalesced write.  o: 64 floats of shared memory private to the warp.
+__device__ __forceinline__ void entropy_row49_warp(float v0, float v1, float* o, int lane, int sym, uint16_t* dst) {
+    const float total = 65536.f;
+    const bool has1 = lane + 32 < 49;
+    float m = fmaxf(v0, v1);
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    const float t0 = expf(v0 - m), t1 = has1 ? expf(v1 - m) : 0.f;
+    __syncwarp();
+    o[lane] = t0;
+    if (has1) o[lane + 32] = t1;
+    __syncwarp();
+    float psum = 0.f;
+    for (int i = 0; i < 49; i++) psum += o[i];   // index order, as the serial row
+    const float dp = total / psum;
+    const int a0 = static_cast<int>(t0 * dp + 0.5);                 // float product, + 0.5 in double, truncation
+    const int a1 = has1 ? static_cast<int>(t1 * dp + 0.5) : 0;
+    int s0 = a0, s1 = a1;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const int u0 = __shfl_up_sync(0xffffffffu, s0, k), u1 = __shfl_up_sync(0xffffffffu, s1, k);
+        if (lane >= k) { s0 += u0; s1 += u1; }
+    }
+    s1 += __shfl_sync(0xffffffffu, s0, 31);
+    __syncwarp();
+    // T[i + 1] = min(prefix(i), total) for i < 48, T[0] = 0, T[49] = total
+    if (lane == 0) { o[0] = 0.f; o[49] = total; }
+    o[lane + 1] = fminf((float)s0, total);
+    if (lane + 32 < 48) o[lane + 33] = fminf((float)s1, total);
+    __syncwarp();
+    if (lane == 0) fixup_row(o, 49, false);
+    __syncwarp();
+    // u16[0..47] = low words of T[1..48], [48] = symbol, [49..51] = bit 16 of T[1..48]
+    const uint32_t e0 = lane < 24 ? (uint32_t)(int)o[2 * lane + 1] : 0u, e1 = lane < 24 ? (uint32_t)(int)o[2 * lane + 2] : 0u;
+    const uint32_t be = __ballot_sync(0xffffffffu, lane < 24 && ((e0 >> 16) & 1u));
+    const uint32_t bo = __ballot_sync(0xffffffffu, lane < 24 && ((e1 >> 16) & 1u));
+    uint32_t ovf[3];
+#pragma unroll
+    for (int mth = 0; mth < 3; mth++) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) wv |= (((be >> (8 * mth + q)) & 1u) << (2 * q)) | (((bo >> (8 * mth + q)) & 1u) << (2 * q + 1));
+        ovf[mth] = wv;
+    }
+    uint32_t word = 0;
+    if (lane < 24) word = (e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << 16);
+    else if (lane == 24) word = ((uint32_t)sym & 0xFFFFu) | (ovf[0] << 16);
+    else if (lane == 25) word = ovf[1] | (ovf[2] << 16);
+    reinterpret_cast<uint32_t*>(dst)[lane] = word;
+    __syncwarp();
+}
+
 // packed code-stream row (coder_internal.h): 7 x u16 low words of T[1..7] + meta = sym | mask << 8 | overflow bits << 9
 __device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst) {
     uint32_t ovf = 0;

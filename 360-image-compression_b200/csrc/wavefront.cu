@@ -25,7 +25,10 @@ namespace cg = cooperative_groups;
 namespace lic360 {
 
 WF_TRACE_DECL
-void wf_trace_set(unsigned long long* buf) { cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf)); }
+void wf_trace_set(unsigned long long* buf, int sel) {
+    cudaMemcpyToSymbol(g_wf_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_wf_trace_sel, &sel, sizeof(sel));
+}
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
 // The inner (h) coordinate of a TMA box must be 16-byte aligned (4 floats; an unaligned start faults with "illegal
@@ -102,13 +105,13 @@ __device__ __forceinline__ WfTile wf_tile(const WfNetDev& net, int dp, int l0 = 
 constexpr int WF_OLD_WARPS = 4;  // warps per CTA; warp w walks the canonical blocks w, w+4, ... that have old terms
 
 __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_constant__ WfNetDev net,
-                                                                  const __grid_constant__ WfMaps maps, int dp) {
+                                                                  const __grid_constant__ WfMaps maps, int dp, int l0) {
     extern __shared__ unsigned char wf_raw[];
     // grid = ((layer, net), chunk, (diagonal, part)): CTAs are dispatched x-fastest, so the tiles of the LARGEST output
     // groups (most old terms) of every layer start first and the light ones fill the tail
-    const WfTile t = wf_tile(net, dp, 0, true);
+    const WfTile t = wf_tile(net, dp, l0, true);
     if (!t.ok) return;  // CTA-uniform
-    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum - dp, WF_TR_OLD0);
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(net.G, t.psum - dp, WF_TR_OLD0);
     const WfLayerDev& L = net.L[t.l];
     const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
     unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
         }
         L.pbuf[t.psum & 1][(((size_t)t.n * L.cpg4 + t.kc) * net.D + t.d) * net.HS + h] = P;
     }
-    if (net.G > 1 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(t.psum - dp, WF_TR_OLD1);
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(net.G, t.psum - dp, WF_TR_OLD1);
 }
 
 // ------------------------------------------------------------------------------------------------ R / Q terms
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(MAXT, 1) wf_prev_kernel(const __grid_constant_
     extern __shared__ float4 wf_psm[];  // [TAPS * cin_g (<= wcap)] weights, then [nqb][32] partials
     const WfTile t = wf_tile(net, dp, l0);
     if (!t.ok) return;
-    if (net.G > 1 && dp == 0 && threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(t.psum, WF_TR_PREV);
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(net.G, t.psum - dp, WF_TR_PREV);
     const WfLayerDev& L = net.L[t.l];
     const int lane = threadIdx.x, jq = threadIdx.y, tid = jq * 32 + lane, nthr = blockDim.x * blockDim.y;
     const int cin_g = L.cin_g, G = net.G, Hp = net.Hp;
@@ -511,12 +514,12 @@ __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const Wf
 // they read the symbols the host decoded a moment ago, so they cannot be computed a step ahead like the other layers'.
 // 25 activations and 25 weight vectors, all in flight together; groups outside [0, G) read the zero padding of the group
 // axis and carry zero weights.  Non-inlined: runs once per step, outside the layer loop.
-__device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d, int h, int tc) {
+__device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d, int h, int tc, int kc = 0) {
     const WfLayerDev& L = net.L[0];
     const int GP = net.G + 2 * WF_GPAD;
     const float* xr = L.xc + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
     const size_t srow = (size_t)(GP - 1) * net.Hp;
-    const float4* w = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + tc) * TAPS;
+    const float4* w = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + tc * L.cpg4 + kc) * TAPS;
     float xv[TAPS];
     float4 wv[TAPS];
 #pragma unroll
@@ -546,7 +549,7 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
         const int target = (psum + 1) * (int)gridDim.x;
         while (*reinterpret_cast<volatile int*>(rows.sync) < target) {}
         __threadfence();
-        WF_TRACE_MIN(psum, WF_TR_ROWS0);
+        WF_TRACE_MIN(net.G, psum, WF_TR_ROWS0);
     }
     __syncthreads();
     const int G = net.G, H = net.H, W = net.W, HW = H * W;
@@ -587,8 +590,50 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
             *rows.done = 0;
             __threadfence_system();
             *reinterpret_cast<volatile int*>(rows.flag) = psum + 1;
-            WF_TRACE_MAX(psum, WF_TR_ROWS1);
+            WF_TRACE_MAX(net.G, psum, WF_TR_ROWS1);
         }
+    }
+}
+
+// Previous-wavefront terms R of step psum1 = p + 1, layers 1..11, evaluated by the chain kernel of step p right behind its CDF
+// rows: the activations of wavefront p are final, the cluster's SMs are idle while the host decodes, and a separate launch for
+// them (wf_prev_kernel) was observed to start only when the concurrently running old-term kernel drained (+30 us on the step).
+// One item = (layer, slab position of step p + 1); arithmetic = one canonical block of 4 channels, taps in (kh, kw, c) order,
+// every tap read unconditionally from the group-padded frame (out-of-range groups are zeros times zero weights).
+__device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int rank, int nc, int psum1, int tid, int nt) {
+    if (psum1 >= net.nsteps) return;
+    if (tid == 0) WF_TRACE_MIN(net.G, psum1 - 1, WF_TR_PREV);
+    const StepDesc s1 = net.steps[psum1];
+    const int HW = net.H * net.W, GP = net.G + 2 * WF_GPAD;
+    const size_t srow = (size_t)(GP - 1) * net.Hp;
+    const int items = (WF_LAYERS - 1) * s1.len;
+    for (int it = rank * nt + tid; it < items; it += nc * nt) {
+        const int l = 1 + it / s1.len, li = it % s1.len;
+        const WfLayerDev& L = net.L[l];
+        const int k = s1.start + li;
+        const int h = __ldg(net.idx + k), d = h + __ldg(net.idx + k + HW), tc = psum1 - d;
+        // tap (kh, kw), s = kh + kw, selects group tc + 3 - s: cell = xr + s * srow + kh, float4 units
+        const float4* xr = reinterpret_cast<const float4*>(L.xc) + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
+        const float4* wr = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + tc) * WF_ROW_F4;
+        float4 xv[TAPS];
+#pragma unroll
+        for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+            for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = __ldcg(xr + (kh + kw) * srow + kh);
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+            for (int kw = 0; kw < 5; kw++) {
+                const float4 x4 = xv[kh * 5 + kw];
+                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float4 w4 = __ldg(wr + (kh * 5 + kw) * 4 + c);
+                    fma4(u, xs[c], w4);
+                }
+            }
+        L.rbuf[psum1 & 1][((size_t)n * net.D + d) * net.HS + h] = make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0
     }
 }
 
@@ -602,7 +647,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const StepDesc sd = net.steps[*net.ctr];
     const int HW = net.H * net.W, par = sd.psum & 1;
-    if (threadIdx.x == 0) WF_TRACE_MIN(sd.psum, WF_TR_CHAIN0);
+    if (threadIdx.x == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_CHAIN0);
     const int per = (sd.len + nc - 1) / nc;
     const int i0 = min(sd.len, rank * per), i1 = min(sd.len, i0 + per), nloc = i1 - i0;
     // plan order is diagonal-major, so the output groups of this CTA's items are the contiguous range [tc_lo, tc_hi]
@@ -704,47 +749,83 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
             else __syncthreads();
         }
     }
-    if (threadIdx.x == 0) WF_TRACE_MAX(sd.psum, WF_TR_CHAIN1);
+    if (threadIdx.x == 0) WF_TRACE_MAX(net.G, sd.psum, WF_TR_CHAIN1);
     if (rows.enabled) wf_chain4_rows(net, rows, sd.psum, sd.start, sd.len, tid, nt);
+    if (rows.enabled && rows.rtail) wf_chain4_rtail(net, n, rank, nc, sd.psum + 1, tid, nt);
 }
 
 // Chain for single-group nets (the importance stream: G = 1, 144 channels).  A step is ONE anti-diagonal (<= min(H,W)
 // positions) and the same-wavefront taps are the five with kh + kw == 4, all on that diagonal, so per layer
 //   Q[pos][oc] = sum over (16-channel block jq | 4-channel chunk, kh, c) of X[pos + kh][c] * W[oc][kh][c]
-// is a small dense product.  The cluster splits the OUTPUT CHUNKS: CTA r owns chunks [r*kpc, (r+1)*kpc) for all
-// positions, keeps its slice of the next layer's weights in shared memory (cp.async, double buffered, issued a layer
-// ahead), and after each cluster barrier copies the diagonal's activations (one contiguous block of the channel-last
-// frame, written by all CTAs of the cluster) into shared memory once.  Warp task = (chunk, canonical block jq, 32
-// positions): activations are conflict-free float4 reads (row stride cin_g + 4), weights are broadcasts.
+// is a small dense product and the layer time is pure latency.  The cluster splits the OUTPUT CHUNKS: CTA r owns chunks
+// [r*kpc, (r+1)*kpc) for all positions and keeps its slice of the next layer's weights in shared memory (cp.async, double
+// buffered, issued a layer ahead).  The diagonal's activations never make a round trip through L2 inside the step: the
+// epilogue of layer l stores its 4 channels straight into the activation tile of EVERY CTA of the cluster (distributed shared
+// memory), the cluster barrier between layers publishes them, and layer l+1 starts computing right behind the barrier.  (The
+// global frames are still written -- later steps' old / previous-wavefront kernels read them -- but nobody waits for that.)
+// Warp task = (canonical block jq, 32 positions) for all kpc chunks of the CTA at once: one set of conflict-free float4
+// activation reads (row stride cin_g + 4) feeds kpc independent accumulator chains, weights are broadcasts.
+constexpr int C1_KB = 3;  // chunks a warp accumulates together
 __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant__ WfNetDev net, int nc, int kpc, int lenp,
-                                                         int cmax) {
+                                                         int cmax, WfRows rows, int r0_inline) {
     extern __shared__ float4 wf_sm1[];
+    __shared__ unsigned long long wbar_mem;  // mbarrier of the weight staging
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
     // programmatic dependent launch: the old-term kernel of the next step may start as soon as every CTA of this kernel is
     // resident (it does not read anything this kernel writes); without that launch attribute this is a no-op
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    if (nc > 1) cluster.barrier_arrive();  // every CTA of the cluster is running before anyone stores into its shared memory
     const StepDesc sd = net.steps[*net.ctr];
+    if (tid == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_CHAIN0);
     const int par = sd.psum & 1, d = sd.psum, len = sd.len;
     const int hmin = max(0, d - net.W + 1);
     const int nqb_max = (cmax + CB - 1) / CB;
     const int xs = cmax + 4;                                            // padded row stride of the activation tile (floats)
+    const int xt_floats = (lenp + 4) * xs;
     float4* wbuf = wf_sm1;                                              // [2][kpc][5][cmax] float4
-    float* xt = reinterpret_cast<float*>(wbuf + (size_t)2 * kpc * 5 * cmax);   // [lenp + 4][xs]
-    float4* part = reinterpret_cast<float4*>(xt + (size_t)(lenp + 4) * xs);   // [kpc][nqb_max][lenp]
+    float* xt = reinterpret_cast<float*>(wbuf + (size_t)2 * kpc * 5 * cmax);   // [2][lenp + 4][xs]: input tile of layer l in half l & 1
+    float4* part = reinterpret_cast<float4*>(xt + (size_t)2 * xt_floats);     // [kpc][nqb_max][lenp]
+    float* ylog = reinterpret_cast<float*>(part + (size_t)kpc * nqb_max * lenp);  // [lenp][52]: last layer's logits, gathered in CTA 0
+    const unsigned wbar = (unsigned)__cvta_generic_to_shared(&wbar_mem);
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // rows hmin-2, hmin-1, hmin+len, hmin+len+1 of the diagonal are outside the image (or outside the frame's written part): zero;
+    // rows 2 .. len+1 are completely rewritten by the producers of every layer
+    for (int e = tid; e < 2 * 4 * xs; e += nt) {
+        const int half = e / (4 * xs), r4 = (e / xs) % 4, c = e % xs;
+        xt[(size_t)half * xt_floats + (size_t)(r4 < 2 ? r4 : len + r4) * xs + c] = 0.f;
+    }
     // slot-0 epilogue item of this thread: (chunk kc0 + it / len, position it % len)
     WfPre pre;
+    // weights of layer l (same-wavefront class, taps (kh, 4 - kh)) of this CTA's chunks: kn * 5 rows of cin_g float4, each one
+    // contiguous in the packed array -> one bulk copy per row, issued by one thread, completing on the mbarrier
+    unsigned wphase = 0;
+    bool wpending = false;
     auto stage_weights = [&](int l) {
         const WfLayerDev& L = net.L[l];
-        if (!L.has_q) return;
         const int kc0 = rank * kpc, kn = max(0, min(kpc, L.cpg4 - kc0));
+        if (!L.has_q || kn == 0) return;
+        wpending = true;
+        if (tid != nt - 32) return;  // lane 0 of the last warp: it has no product task when nqb * npg < nwarps
         const int cg = L.cin_g;
         const float4* src = reinterpret_cast<const float4*>(L.wq) + ((size_t)(net.nsets + n) * L.nchunk + kc0) * TAPS * cg;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(wbuf + (size_t)(l & 1) * kpc * 5 * cmax);
-        for (int e = tid; e < kn * 5 * cg; e += nt) {
-            const int c = e % cg, kh = (e / cg) % 5, k = e / (5 * cg);
-            cp_async16(dst + 16u * ((k * 5 + kh) * cmax + c), src + ((size_t)k * TAPS + kh * 5 + 4 - kh) * cg + c);
+        mbar_expect_tx(wbar, kn * 5 * cg * 16);
+        for (int e = 0; e < kn * 5; e++) {
+            const int kh = e % 5, k = e / 5;
+            bulk_load(dst + 16u * (unsigned)(e * cmax), src + ((size_t)k * TAPS + kh * 5 + 4 - kh) * cg, cg * 16, wbar);
         }
+    };
+    auto wait_weights = [&]() {
+        if (!wpending) return;
+        mbar_wait(wbar, wphase);
+        wphase ^= 1;
+        wpending = false;
     };
     auto prefetch = [&](int l) {
         const WfLayerDev& L = net.L[l];
@@ -752,7 +833,10 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
         if (tid >= kn * len) return;
         const int kc = kc0 + tid / len, h = hmin + tid % len;
         pre.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
-        pre.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+        // layer 0 reads the symbols the scatter kernel wrote a moment ago: its previous-wavefront terms are evaluated here instead
+        // of by one more launch in front of the chain
+        if (l == 0 && r0_inline) pre.rr = wf_r_layer0_c1(net, n, d, h, 0, kc);
+        else pre.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
         const size_t fc = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -763,59 +847,77 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
         }
     };
     stage_weights(1);
-    asm volatile("cp.async.commit_group;\n" ::);
     prefetch(0);
+    // debug timeline (LIC360_WF_TRACE=2): ns spent by CTA 0 in the phases of every layer, accumulated behind the step slots
+    const bool phase_trace = g_wf_trace && g_wf_trace_sel == 1 && blockIdx.x == 0 && tid == 0;
+    unsigned long long tph = 0;
+    auto phase = [&](int l, int ph) {
+        if (!phase_trace) return;
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        if (ph >= 0) atomicAdd(g_wf_trace + (size_t)(net.nsteps + 2) * WF_TR_SLOTS + l * 4 + ph, t_ - tph);
+        tph = t_;
+    };
+    if (nc > 1) cluster.barrier_wait();
+    phase(0, -1);
     for (int l = 0; l < WF_LAYERS; l++) {
         const WfLayerDev& L = net.L[l];
         const int kc0 = rank * kpc, kn = max(0, min(kpc, L.cpg4 - kc0));
         if (l >= 1 && l + 1 < WF_LAYERS) {  // weights of layer l+1 (layer 1 was staged before the loop)
             stage_weights(l + 1);
-            asm volatile("cp.async.commit_group;\n" ::);
         }
+        phase(l, 0);
         if (L.has_q && kn > 0) {
             const int cg = L.cin_g;
-            // the diagonal's activations, rows hmin-2 .. hmin+len+1: one contiguous block of the channel-last frame
-            const float4* xsrc = reinterpret_cast<const float4*>(L.xc + wf_fc_index(net.Dp, net.Hp, 1, cg, n, d, 0, hmin - 2));
-            const int row_f4 = cg >> 2;
-            for (int e = tid; e < (len + 4) * row_f4; e += nt) {
-                const int r = e / row_f4, c4 = e % row_f4;
-                *reinterpret_cast<float4*>(xt + (size_t)r * xs + 4 * c4) = __ldcg(xsrc + e);
-            }
-            __syncthreads();
+            const float* xl = xt + (size_t)(l & 1) * xt_floats;  // rows hmin-2 .. hmin+len+1, stored by the previous layer's epilogues
             const float4* wl = wbuf + (size_t)(l & 1) * kpc * 5 * cmax;
             const int npg = (len + 31) >> 5, nqb = L.nqb;
-            for (int wt = warp; wt < kn * nqb * npg; wt += nwarps) {
-                const int pg = wt % npg, jq = (wt / npg) % nqb, k = wt / (npg * nqb);
-                const int pos = pg * 32 + lane;
-                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pos < len) {
+            for (int k0 = 0; k0 < kn; k0 += C1_KB) {
+                const int kb = min(C1_KB, kn - k0);
+                for (int wt = warp; wt < nqb * npg; wt += nwarps) {
+                    const int pg = wt % npg, jq = wt / npg;
+                    const int pos = pg * 32 + lane;
+                    if (pos >= len) continue;
+                    float4 u[C1_KB];
+#pragma unroll
+                    for (int k = 0; k < C1_KB; k++) u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int cend = min((jq + 1) * CB, cg);
                     for (int c0 = jq * CB; c0 < cend; c0 += 4) {
                         float4 xv[5];
 #pragma unroll
-                        for (int kh = 0; kh < 5; kh++) xv[kh] = *reinterpret_cast<const float4*>(xt + (size_t)(pos + kh) * xs + c0);
+                        for (int kh = 0; kh < 5; kh++) xv[kh] = *reinterpret_cast<const float4*>(xl + (size_t)(pos + kh) * xs + c0);
 #pragma unroll
                         for (int kh = 0; kh < 5; kh++) {
-                            const float4* wr = wl + (size_t)(k * 5 + kh) * cmax + c0;
                             const float x4[4] = {xv[kh].x, xv[kh].y, xv[kh].z, xv[kh].w};
 #pragma unroll
                             for (int c = 0; c < 4; c++) {
-                                const float4 w4 = wr[c];
-                                fma4(u, x4[c], w4);
+#pragma unroll
+                                for (int k = 0; k < C1_KB; k++) {
+                                    if (k >= kb) continue;  // warp-uniform
+                                    const float4 w4 = wl[(size_t)((k0 + k) * 5 + kh) * cmax + c0 + c];
+                                    fma4(u[k], x4[c], w4);
+                                }
                             }
                         }
                     }
-                    part[((size_t)k * nqb_max + jq) * lenp + pos] = u;
+#pragma unroll
+                    for (int k = 0; k < C1_KB; k++)
+                        if (k < kb) part[((size_t)(k0 + k) * nqb_max + jq) * lenp + pos] = u[k];
                 }
             }
             __syncthreads();
         }
+        phase(l, 1);
+        // ranks that consume this layer's output in the next layer (those that own output chunks there)
+        const int nranks_next = (l + 1 < WF_LAYERS && net.L[l + 1].has_q) ? min(nc, (net.L[l + 1].cpg4 + kpc - 1) / kpc) : 0;
+        float* xnext = xt + (size_t)((l + 1) & 1) * xt_floats;
         for (int it = tid; it < kn * len; it += nt) {
             const int k = it / len, pos = it % len, kc = kc0 + k, h = hmin + pos;
             WfPre p = pre;
             if (it != tid) {  // further slots (more items than threads): nothing was prefetched
                 p.pr = __ldg(L.pbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
-                p.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
+                if (l == 0 && r0_inline) p.rr = wf_r_layer0_c1(net, n, d, h, 0, kc);
+                else p.rr = __ldg(L.rbuf[par] + (((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h);
                 const size_t fcr = wf_fc_index(net.Dp, net.Hp, 1, L.cout_g, n, d, 0, h) + kc * 4;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -842,22 +944,63 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
                 if (L.slope) y = y > 0.f ? y : y * p.sl[q];
                 if (L.rc) y = y + p.rs[q];
                 v[q] = y;
-                if (L.op) L.op[wf_fp_index(net.D, net.HS, L.Cout, n, kc * 4 + q, d, h)] = y;
             }
+            const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+            // next layer's input tile in every consuming CTA (cin_g of the next layer == cout_g of this one, a multiple of 4 there)
+            if (nranks_next > 0 && kc * 4 + 3 < L.cout_g) {
+                float* dst = xnext + (size_t)(pos + 2) * xs + kc * 4;
+                if (nc > 1) {
+                    for (int r = 0; r < nranks_next; r++) *reinterpret_cast<float4*>(cluster.map_shared_rank(dst, r)) = v4;
+                } else {
+                    *reinterpret_cast<float4*>(dst) = v4;
+                }
+            }
+            if (rows.enabled && l == WF_LAYERS - 1) {  // logits of the CDF rows, gathered in CTA 0
+                float* yd = ylog + (size_t)pos * 52 + kc * 4;
+                if (nc > 1) yd = cluster.map_shared_rank(yd, 0);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (kc * 4 + q < L.cout_g) yd[q] = v[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (kc * 4 + q < L.cout_g && L.op) L.op[wf_fp_index(net.D, net.HS, L.Cout, n, kc * 4 + q, d, h)] = v[q];
             if ((L.cout_g & 3) == 0) {
-                *reinterpret_cast<float4*>(L.oc + fc) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(L.oc + fc) = v4;
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     if (kc * 4 + q < L.cout_g) L.oc[fc + q] = v[q];
             }
         }
+        phase(l, 2);
         if (l + 1 < WF_LAYERS) {
             prefetch(l + 1);
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            if (nc > 1) cg::this_cluster().sync();
+            wait_weights();
+            if (nc > 1) cluster.sync();
             else __syncthreads();
         }
+        phase(l, 3);
+    }
+    if (tid == 0) WF_TRACE_MAX(net.G, sd.psum, WF_TR_CHAIN1);
+    if (!rows.enabled) return;
+    // CDF rows of the step (EntropyTable over the 49 logits of every position): the last layer's epilogues stored the logits into
+    // CTA 0's shared memory; one warp per symbol, then the host flag -- no further launch on the critical path of the stream
+    if (nc > 1) cluster.sync();
+    else __syncthreads();
+    if (rank != 0) return;
+    if (tid == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_ROWS0);
+    float* scratch = reinterpret_cast<float*>(part) + warp * 64;  // the partial sums are dead by now
+    for (int l = warp; l < len; l += nwarps) {
+        const int th = __ldg(net.idx + sd.start + l);
+        const float* yp = ylog + (size_t)(th - hmin) * 52;
+        entropy_row49_warp(yp[lane], lane + 32 < 49 ? yp[lane + 32] : -INFINITY, scratch, lane, 0, rows.rows + (size_t)l * 64);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        *reinterpret_cast<volatile int*>(rows.flag) = sd.psum + 1;
+        WF_TRACE_MAX(net.G, sd.psum, WF_TR_ROWS1);
     }
 }
 
@@ -974,13 +1117,13 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         e.c1_cmax = 4;
         for (int l = 1; l < WF_LAYERS; l++) { e.chain1 = e.chain1 && (n.L[l].cin_g & 3) == 0; e.c1_cmax = std::max(e.c1_cmax, n.L[l].cin_g); }
         if (getenv("LIC360_WF_GENERIC_CHAIN")) e.chain4 = e.chain1 = false;
-        e.r0_inline = e.chain4 && n.L[0].cin_g == 1 && n.L[0].cpg4 == 1 && !getenv("LIC360_WF_R0_KERNEL");
+        e.r0_inline = ((e.chain4 && n.L[0].cpg4 == 1) || e.chain1) && n.L[0].cin_g == 1 && !getenv("LIC360_WF_R0_KERNEL");
         if (e.chain4) e.chain_smem = (size_t)2 * G * WF_ROW_F4 * sizeof(float4);
         if (e.chain1) {
             e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
             e.c1_lenp = ((max_len + 31) / 32) * 32;
-            const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)(e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
-                              (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4);
+            const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)2 * (e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
+                              (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4) + (size_t)e.c1_lenp * 52 * sizeof(float);
             if (sm <= 200 * 1024) { e.chain_smem = sm; e.chain_threads = 384; }
             else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
         }
@@ -1039,7 +1182,6 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(WF_LAYERS * n.nsets, e.cpg4_max, n.ndiag * n.parts);
     cfg.blockDim = dim3(32, WF_OLD_WARPS);
     cfg.dynamicSmemBytes = e.old_smem;
     cfg.stream = s;
@@ -1047,9 +1189,19 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start once the previous kernel's CTAs have all
     attr[0].val.programmaticStreamSerializationAllowed = 1;          // executed griddepcontrol.launch_dependents
     cfg.attrs = attr;
-    cfg.numAttrs = programmatic ? 1 : 0;
-    g_launches++;
-    return cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp);
+    // LIC360_WF_OLD_SPLIT=k (experiment): k launches over layer ranges, so that the grid drains k times per step and a
+    // cluster launch of the other bitstream's chain, which needs whole SMs, gets a window
+    static const int split_env = getenv("LIC360_WF_OLD_SPLIT") ? std::max(1, std::min(WF_LAYERS, atoi(getenv("LIC360_WF_OLD_SPLIT")))) : 1;
+    const int split = n.G > 1 ? split_env : 1;
+    for (int k = 0; k < split; k++) {
+        const int l0 = k * WF_LAYERS / split, l1 = (k + 1) * WF_LAYERS / split;
+        cfg.gridDim = dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * n.parts);
+        cfg.numAttrs = programmatic && k == 0 ? 1 : 0;
+        g_launches++;
+        const cudaError_t err = cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream_t s) {
@@ -1066,7 +1218,7 @@ cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream
 cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows) {
     WfRows r;
     memset(&r, 0, sizeof(r));
-    if (rows && e.chain4) r = *rows;
+    if (rows && (e.chain4 || e.chain1)) r = *rows;
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1081,7 +1233,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* row
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
     if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r, (int)(e.r0_inline && r.enabled));
-    if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax);
+    if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax, r, (int)(e.r0_inline && r.enabled));
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }
 

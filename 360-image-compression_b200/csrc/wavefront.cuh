@@ -50,6 +50,7 @@ struct WfRows {
     int* sync;            // monotone counter: all nets have finished layer 11 of step p when it reaches (p + 1) * gridDim.x
     float s2;
     int enabled;
+    int rtail;            // the chain kernel also evaluates the previous-wavefront terms of the NEXT step (layers 1..11) behind the rows
 };
 
 struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer, box {40 h, 9 d, 4 c}
@@ -95,19 +96,19 @@ __host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int G, int cpg, in
 // Debug timeline (LIC360_WF_TRACE=1): per step 8 slots of %globaltimer stamps.  Each translation unit has its own copy of
 // the device pointer (no relocatable device code); wf_trace_set() / codec_trace_set() point both at the same buffer.
 enum { WF_TR_SCATTER = 0, WF_TR_PREV, WF_TR_CHAIN0, WF_TR_CHAIN1, WF_TR_ROWS0, WF_TR_ROWS1, WF_TR_OLD0, WF_TR_OLD1, WF_TR_SLOTS };
-void wf_trace_set(unsigned long long* buf);
-#define WF_TRACE_DECL static __device__ unsigned long long* g_wf_trace = nullptr;
-#define WF_TRACE_MIN(step, slot)                                                                          \
+void wf_trace_set(unsigned long long* buf, int sel);  // sel: 0 = trace the multi-group (code) stream, 1 = the single-group (importance) stream
+#define WF_TRACE_DECL static __device__ unsigned long long* g_wf_trace = nullptr; static __device__ int g_wf_trace_sel = 0;
+#define WF_TRACE_MIN(G, step, slot)                                                                       \
     do {                                                                                                  \
-        if (g_wf_trace) {                                                                                 \
+        if (g_wf_trace && ((G) > 1 ? 0 : 1) == g_wf_trace_sel) {                                                                                 \
             unsigned long long t_;                                                                        \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
             atomicMin(g_wf_trace + (size_t)(step) * WF_TR_SLOTS + (slot), t_);                            \
         }                                                                                                 \
     } while (0)
-#define WF_TRACE_MAX(step, slot)                                                                          \
+#define WF_TRACE_MAX(G, step, slot)                                                                       \
     do {                                                                                                  \
-        if (g_wf_trace) {                                                                                 \
+        if (g_wf_trace && ((G) > 1 ? 0 : 1) == g_wf_trace_sel) {                                                                                 \
             unsigned long long t_;                                                                        \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
             atomicMax(g_wf_trace + (size_t)(step) * WF_TR_SLOTS + (slot), t_);                            \

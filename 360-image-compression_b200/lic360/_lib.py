@@ -69,6 +69,8 @@ SIGNATURES = {
     "lic360_coder_finish_mem": (_L, [_P]),
     "lic360_coder_get_bytes": (_L, [_P, _P, _L]),
     "lic360_coder_start_decoder_mem": (_I, [_P, _P, _L]),
+    "lic360_coder_encode_rows": (_I, [_P, _P, _I, _I]),
+    "lic360_coder_decode_rows": (_I, [_P, _P, _I, _I, _P]),
     "lic360_codec_create": (_P, [_I, _I, _I]),
     "lic360_codec_destroy": (None, [_P]),
     "lic360_codec_set_layer": (_I, [_P, _I, _I, _P, _P, _P]),

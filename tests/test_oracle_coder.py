@@ -146,3 +146,95 @@ def test_file_api_matches_reference_layout(lib_built, tmp_path):
     c.start_decoder()
     out = c.decodes_mask(torch.from_numpy(tab), 8, torch.from_numpy(mask), 1200)
     assert out.shape == (1200,) and np.array_equal(out.numpy(), np.where(mask > 0.5, lab, 3.5).astype(np.float32))
+
+
+# ---- packed CDF rows (the format the fused codec's kernels hand to the host coder) -----------------------------------
+def _pack_rows(tab, lab, mask, kind):
+    """numpy restatement of pack_gmm_row (tables_dev.cuh) / the importance-row packing (codec.cu), include/lic360_b200.h."""
+    rows = tab.shape[0]
+    if kind == 0:
+        out = np.zeros((rows, 8), np.uint16)
+        inner = tab[:, 1:8].astype(np.int64)
+        out[:, :7] = (inner & 0xFFFF).astype(np.uint16)
+        ovf = (((inner >> 16) & 1) << np.arange(7)).sum(1)
+        m = np.ones(rows, np.int64) if mask is None else (mask >= 0.5).astype(np.int64)
+        out[:, 7] = ((lab.astype(np.int64) & 7) | (m << 8) | (ovf << 9)).astype(np.uint16)
+    else:
+        out = np.zeros((rows, 64), np.uint16)
+        inner = tab[:, 1:49].astype(np.int64)
+        out[:, :48] = (inner & 0xFFFF).astype(np.uint16)
+        out[:, 48] = lab.astype(np.uint16)
+        bits = (inner >> 16) & 1
+        for w in range(3):
+            out[:, 49 + w] = (bits[:, 16 * w:16 * w + 16] << np.arange(16)).sum(1).astype(np.uint16)
+    return np.ascontiguousarray(out)
+
+
+def _overflow_tables(r, rows, ncode):
+    """rows whose last interior bin is 65536 itself (bit 16 set, low word 0: an empty top symbol), the one value of a valid table that
+    needs the 17th bit of the packed format"""
+    tab = random_tables(r, rows, ncode).astype(np.int64)
+    k = rows // 3
+    tab[:k, -2] = 65536
+    return tab.astype(np.int32)
+
+
+@pytest.mark.parametrize("kind,ncode,rows,masked", [(0, 8, 6000, True), (0, 8, 1500, False), (1, 49, 900, False), (0, 8, 0, True)])
+def test_packed_rows_equal_table_path(kind, ncode, rows, masked, lib_built):
+    L = _product_coder()
+    r = rng(100 + kind + rows)
+    tab = random_tables(r, rows, ncode)
+    lab = r.integers(0, ncode, rows).astype(np.int32)
+    if rows:  # make sure every symbol value and the extreme bins occur
+        lab[:ncode] = np.arange(ncode)
+    mask = (r.random(rows) > 0.35).astype(np.float32) if masked else None
+    want = _product_encode(tab, lab, mask)   # pinned against the reference coder by test_roundtrip / test_golden
+    packed = _pack_rows(tab, lab, mask, kind)
+    h = ctypes.c_void_p(L.lic360_coder_create(b"unused", 3.5))
+    assert L.lic360_coder_start_encoder_mem(h) == 0
+    for a in range(0, rows, 257):  # step-wise, as the codec calls it
+        chunk = np.ascontiguousarray(packed[a:a + 257])
+        assert L.lic360_coder_encode_rows(h, chunk.ctypes.data, chunk.shape[0], kind) == 0, L.lic360_last_error()
+    n = L.lic360_coder_finish_mem(h)
+    buf = np.zeros(max(n, 1), np.uint8)
+    L.lic360_coder_get_bytes(h, buf.ctypes.data, n)
+    assert buf[:n].tobytes() == want
+    # decode: the rows of a decoder carry no symbol
+    blank = _pack_rows(tab, np.zeros_like(lab), mask, kind)
+    arr = np.frombuffer(want, np.uint8).copy()
+    assert L.lic360_coder_start_decoder_mem(h, arr.ctypes.data, len(arr)) == 0
+    out = np.full(rows, -1, np.float32)
+    for a in range(0, rows, 257):
+        chunk = np.ascontiguousarray(blank[a:a + 257])
+        o = out[a:a + 257]
+        assert L.lic360_coder_decode_rows(h, chunk.ctypes.data, chunk.shape[0], kind, o.ctypes.data) == 0, L.lic360_last_error()
+    expect = lab.astype(np.float32) if mask is None else np.where(mask > 0.5, lab, 3.5).astype(np.float32)
+    assert np.array_equal(out, expect)
+    L.lic360_coder_destroy(h)
+
+
+def test_packed_rows_overflow_bins_and_corrupt_stream(lib_built):
+    L = _product_coder()
+    r = rng(77)
+    rows = 3000
+    tab = _overflow_tables(r, rows, 8)
+    assert (np.diff(tab.astype(np.int64), axis=1)[:, :-1] > 0).all() and (tab[:rows // 3, 7] == 65536).all()
+    lab = r.integers(0, 7, rows).astype(np.int32)   # symbol 7 is empty in the overflow rows: never coded there
+    mask = np.ones(rows, np.float32)
+    packed, blank = _pack_rows(tab, lab, mask, 0), _pack_rows(tab, np.zeros_like(lab), mask, 0)
+    h = ctypes.c_void_p(L.lic360_coder_create(b"unused", 3.5))
+    L.lic360_coder_start_encoder_mem(h)
+    assert L.lic360_coder_encode_rows(h, packed.ctypes.data, rows, 0) == 0, L.lic360_last_error()
+    n = L.lic360_coder_finish_mem(h)
+    buf = np.zeros(n, np.uint8)
+    L.lic360_coder_get_bytes(h, buf.ctypes.data, n)
+    L.lic360_coder_start_decoder_mem(h, buf.ctypes.data, n)
+    out = np.zeros(rows, np.float32)
+    assert L.lic360_coder_decode_rows(h, blank.ctypes.data, rows, 0, out.ctypes.data) == 0, L.lic360_last_error()
+    assert np.array_equal(out, lab.astype(np.float32))
+    # calling without a started decoder / with a bad kind is an error, not a crash
+    h2 = ctypes.c_void_p(L.lic360_coder_create(b"unused", 3.5))
+    assert L.lic360_coder_decode_rows(h2, blank.ctypes.data, rows, 0, out.ctypes.data) != 0
+    assert L.lic360_coder_decode_rows(h, blank.ctypes.data, rows, 2, out.ctypes.data) != 0
+    L.lic360_coder_destroy(h)
+    L.lic360_coder_destroy(h2)
