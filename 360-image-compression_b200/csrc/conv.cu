@@ -109,7 +109,7 @@ __device__ __forceinline__ void ec_taps_fma(const float* xr, const float4* wA, c
     }
 }
 
-__global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a, int pair) {
     extern __shared__ float4 smem_f4[];
     float* xs = reinterpret_cast<float*>(smem_f4);  // [CB][XH][XW]
     float4* ws4 = smem_f4 + (CB * XH * XW) / 4;     // [EC_CHUNKS][CB][TAPS] float4
@@ -118,7 +118,15 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
     const int tx = tid & 7, ty = (tid >> 3) & 7, tz = tid >> 6;
     const int tiles_w = (a.W + TW - 1) / TW;
     const int w0 = (blockIdx.x % tiles_w) * TW, h0 = (blockIdx.x / tiles_w) * TH;
-    const int ytile = (int)gridDim.y - 1 - (int)blockIdx.y;  // heaviest (largest g_out) tiles first
+    // The K extent of a y tile grows with its output groups (old terms: g_in <= g_out + 2), so a CTA takes the PAIR (heaviest
+    // remaining, lightest remaining) = y tiles (ny - 1 - b, b): every CTA of the launch then has nearly the same work and one wave
+    // of CTAs finishes together instead of leaving a 20% tail of idle SMs behind the heavy tiles.
+    const int ny = (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS;
+    // (pair == 0: small grids that do not fill the machine anyway keep one y tile per CTA, heaviest first.)
+  for (int pass = 0; pass < 1 + pair; pass++) {
+    const int ytile = pass == 0 ? ny - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    if (pass == 1 && ytile >= ny - 1 - (int)blockIdx.y) break;  // middle tile of an odd count: done in pass 0
+    if (pass == 1) __syncthreads();                             // everyone is done with the staging buffers of pass 0
     const int chunk0 = ytile * EC_CHUNKS;
     const int n = blockIdx.z, set = n / a.per;
     const int Cin = a.Cin, H = a.H, W = a.W;
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
             }
         }
     }
+  }  // pass
 }
 
 // EC, second pass: adds the previous-wavefront (R) and same-wavefront (Q) terms -- every tap reads the cin_g channels
@@ -532,8 +541,10 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid(((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH), (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, a.N);
-    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a);
+    const int ny = (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, nxy = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
+    const int pair = (long long)nxy * ny * a.N > 2 * 148 ? 1 : 0;  // more than one wave of CTAs (2 per SM): balance them in pairs
+    dim3 grid(nxy, pair ? (ny + 1) / 2 : ny, a.N);
+    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a, pair);
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
