@@ -54,6 +54,7 @@ struct NetDesc {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prof[6] = {nullptr};
     int* ctr_dev = nullptr;             // current wavefront step (device counter)
     int* done_dev = nullptr;            // CTA counter of the rows kernel
+    int* arrived_dev = nullptr;         // CTA counter of the scatter kernel (the last CTA advances ctr_dev)
     int* sync_dev = nullptr;            // code stream: monotone cross-cluster counter of the chain kernel's rows phase
     int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
     int* go_host = nullptr;             // mapped pinned: the stream may run step p once this is >= p (launch-ahead, decode_stream)
@@ -172,30 +173,39 @@ __global__ void imp_rows_kernel(const float* __restrict__ y, const float* __rest
 }
 
 // TileInput of the previous step read from mapped pinned memory (tile_input_cuda.cu:27-43) into both layouts of the
-// engine's input frame, replicated for the nsets nets; no-op at step 0
+// engine's input frame, replicated for the nsets nets; no-op at step 0.  This is the FIRST kernel of a step and it also advances
+// the device step counter: every CTA reads the old value on entry (step = old + 1), the last CTA to finish publishes the new
+// one, and every later kernel of the step reads it at its own start -- no one-thread "advance" launch at the end of the step.
 __global__ void scatter_prev_kernel(const float* __restrict__ syms, float* __restrict__ fp0, float* __restrict__ fc0,
-                                    const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps, const int* __restrict__ ctr,
-                                    int G, int H, int W, int D, int HS, int Dp, int Hp, float bias, float scale, int rep,
-                                    float* __restrict__ keep) {
-    const int c = *ctr;
+                                    const int32_t* __restrict__ idx, const StepDesc* __restrict__ steps, int* __restrict__ ctr,
+                                    int* __restrict__ arrived, int G, int H, int W, int D, int HS, int Dp, int Hp, float bias,
+                                    float scale, int rep, float* __restrict__ keep) {
+    const int c = *reinterpret_cast<volatile int*>(ctr) + 1;
     if (threadIdx.x == 0 && blockIdx.x == 0) WF_TRACE_MIN(G, c, WF_TR_SCATTER);
-    if (c == 0) return;
-    const StepDesc d = steps[c - 1];
-    const int HW = H * W;
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < d.len; l += gridDim.x * blockDim.x) {
-        const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
-        const int tc = d.psum - th - tw;
-        const float s = syms[l];
-        const float v = fmaf(scale, s, bias);
-        for (int r = 0; r < rep; r++) {
-            fp0[wf_fp_index(D, HS, G, r, tc, th + tw, th)] = v;
-            fc0[wf_fc_index(Dp, Hp, G, 1, r, th + tw, tc, th)] = v;
+    if (c > 0) {
+        const StepDesc d = steps[c - 1];
+        const int HW = H * W;
+        for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < d.len; l += gridDim.x * blockDim.x) {
+            const int th = __ldg(idx + d.start + l), tw = __ldg(idx + d.start + l + HW);
+            const int tc = d.psum - th - tw;
+            const float s = syms[l];
+            const float v = fmaf(scale, s, bias);
+            for (int r = 0; r < rep; r++) {
+                fp0[wf_fp_index(D, HS, G, r, tc, th + tw, th)] = v;
+                fc0[wf_fc_index(Dp, Hp, G, 1, r, th + tw, tc, th)] = v;
+            }
+            if (keep) keep[th * W + tw] = s;  // importance stream: the decoded level itself
         }
-        if (keep) keep[th * W + tw] = s;  // importance stream: the decoded level itself
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(arrived, 1) == (int)gridDim.x - 1) {
+            *arrived = 0;
+            *ctr = c;
+        }
     }
 }
-
-__global__ void advance_kernel(int* ctr) { *ctr = *ctr + 1; }
 
 // code = frame[0:1] + 3.5 * mask (lic360_demo.py:236-237), gathered from the channel-last engine frame
 __global__ void finish_code_kernel(const float* __restrict__ fc0, const float* __restrict__ mask, float* __restrict__ out,
@@ -390,10 +400,10 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     const int tgrid = (n.max_len + 127) / 128;
     if (ev) LIC360_CUDA(cudaEventRecord(ev[0], s));
     if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.G, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.arrived_dev, n.G, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
     else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, 1, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.arrived_dev, 1, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     WF_DEBUG_SYNC("scatter kernel");
@@ -458,8 +468,6 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     }
     WF_DEBUG_SYNC("old-term kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[5], s));
-    advance_kernel<<<1, 1, 0, s>>>(n.ctr_dev);
-    LAUNCH_CHECK();
     return LIC360_OK;
 }
 
@@ -520,6 +528,7 @@ static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int pri
     for (int i = 0; i < 6; i++) LIC360_CUDA(cudaEventCreate(&n.ev_prof[i]));
     LIC360_CUDA(cudaMalloc(&n.ctr_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.arrived_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.sync_dev, sizeof(int)));
     LIC360_CUDA(cudaHostAlloc(&n.flag_host, sizeof(int), cudaHostAllocMapped));
     LIC360_CUDA(cudaHostAlloc(&n.go_host, 64, cudaHostAllocMapped));
@@ -537,7 +546,7 @@ static int ctx_buffers(NetDesc& n) {
 }
 
 static void ctx_free(NetDesc& n) {
-    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host); cudaFreeHost(n.go_host);
+    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.arrived_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host); cudaFreeHost(n.go_host);
     cudaFree(n.rows_dev); cudaFreeHost(n.rows_host); cudaFreeHost(n.rows_step_host); cudaFreeHost(n.syms_host);
     if (n.ev_fork) cudaEventDestroy(n.ev_fork);
     if (n.ev_join) cudaEventDestroy(n.ev_join);
@@ -742,10 +751,10 @@ static int final_scatter(lic360_codec* c, NetDesc& n, bool is_code) {
     const int tgrid = (n.max_len + 127) / 128;
     cudaStream_t s = n.stream;
     if (is_code)
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.G, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.arrived_dev, n.G, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -3.5f, 1.0f, 3, nullptr);
     else
-        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, 1, n.H, n.W,
+        scatter_prev_kernel<<<tgrid, 128, 0, s>>>(n.syms_host, n.wf.fp[0], n.wf.fc[0], n.idx_dev, n.steps_dev, n.ctr_dev, n.arrived_dev, 1, n.H, n.W,
                                                   w.D, w.HS, w.Dp, w.Hp, -1.0f, (float)(2. / (48 - 1.)), 1, c->levels_dev);
     LAUNCH_CHECK();
     return LIC360_OK;
@@ -774,10 +783,11 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     GoRelease go_release{n.go_host};
     n.t_host_coder = 0; n.t_gpu_wait = 0;
     LIC360_CUDA(wf_clear(n.wf, s));
-    LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0xFF, sizeof(int), s));  // -1: the scatter kernel of step p makes it p
     LIC360_CUDA(cudaMemsetAsync(n.done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.arrived_dev, 0, sizeof(int), s));
     LIC360_CUDA(cudaMemsetAsync(n.sync_dev, 0, sizeof(int), s));
-    LIC360_CUDA(wf_launch_old(n.wf, 0, s));  // old terms of step 0 (all zero, but it keeps the schedule uniform)
+    LIC360_CUDA(wf_launch_old(n.wf, 1, s));  // old terms of step 0 = counter (-1) + 1 (all zero, but it keeps the schedule uniform)
     if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
     auto wait_levels = [&](int p) -> int {  // code stream: the importance levels step p needs are decoded
