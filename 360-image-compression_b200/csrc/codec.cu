@@ -57,6 +57,7 @@ struct NetDesc {
     int* arrived_dev = nullptr;         // CTA counter of the scatter kernel (the last CTA advances ctr_dev)
     int* sync_dev = nullptr;            // code stream: monotone cross-cluster counter of the chain kernel's rows phase
     int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
+    int nflags = 1;                     // host flags the rows producer raises (one per CTA of the fused code-stream chain)
     int* go_host = nullptr;             // mapped pinned: the stream may run step p once this is >= p (launch-ahead, decode_stream)
     uint16_t* rows_dev = nullptr;       // encode: all rows of the stream
     uint16_t* rows_host = nullptr;      // pinned
@@ -423,6 +424,8 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
         rows.sync = n.sync_dev; rows.s2 = (float)(1. / sqrt(2.0)); rows.enabled = 1;
     }
     // code stream: the chain kernel also leaves the previous-wavefront terms of the next step behind (no launch, no side branch)
+    n.nflags = fused_rows && is_code ? n.wf.dev.nsets * n.wf.cluster : 1;
+    if (n.nflags > 64) { set_error("codec: %d chain CTAs exceed the 64 host flags", n.nflags); return LIC360_ERR_ARG; }
     const bool rtail = fused_rows && is_code && n.wf.chain4 && !getenv("LIC360_WF_PREV_KERNEL");
     rows.rtail = rtail ? 1 : 0;
     LIC360_CUDA(wf_launch_chain(n.wf, s, fused_rows ? &rows : nullptr));
@@ -530,7 +533,7 @@ static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int pri
     LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.arrived_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.sync_dev, sizeof(int)));
-    LIC360_CUDA(cudaHostAlloc(&n.flag_host, sizeof(int), cudaHostAllocMapped));
+    LIC360_CUDA(cudaHostAlloc(&n.flag_host, 64 * sizeof(int), cudaHostAllocMapped));
     LIC360_CUDA(cudaHostAlloc(&n.go_host, 64, cudaHostAllocMapped));
     *n.go_host = 0;
     n.coder = lic360_coder_create("", fill);
@@ -725,12 +728,18 @@ struct GoRelease {
 static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
     volatile int* f = n.flag_host;
     const auto t0 = clk::now();
-    for (unsigned spins = 1; *f != p + 1; spins++) {
+    const int nf = n.nflags;
+    auto ready = [&]() {
+        for (int i = 0; i < nf; i++)
+            if (f[i] != p + 1) return false;
+        return true;
+    };
+    for (unsigned spins = 1; !ready(); spins++) {
         if ((spins & 0x3FFF) == 0) {
             if (c->abort_flag.load()) { set_error("codec: aborted (the other stream failed)"); return LIC360_ERR_CUDA; }
             const cudaError_t e = cudaStreamQuery(n.stream);
             if (e == cudaSuccess) {
-                if (*f == p + 1) break;
+                if (ready()) break;
                 set_error("codec: step %d finished without producing its rows", p);
                 return LIC360_ERR_CUDA;
             }
@@ -766,7 +775,7 @@ static int final_scatter(lic360_codec* c, NetDesc& n, bool is_code) {
 static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaStream_t s = n.stream;
     int rc = LIC360_OK;
-    *n.flag_host = 0;
+    for (int i = 0; i < 64; i++) n.flag_host[i] = 0;
     // Launch-ahead (experiment, LIC360_WF_LAUNCH_AHEAD=1; measured ~1 ms SLOWER per 512x1024 decode than launching each step's
     // graph when its symbols are ready, so it is off by default): while the GPU works on step p the host already enqueues
     // [wait until *go >= p+1][graph of step p+1]; once the symbols of step p are decoded (and, for the code stream, the importance

@@ -554,11 +554,13 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
     __syncthreads();
     const int G = net.G, H = net.H, W = net.W, HW = H * W;
     const float* y = net.L[WF_LAYERS - 1].oc;
-    const int total = ((len * 8 + 31) >> 5) << 5;  // whole warps: 8 lanes per symbol, lane j computes bin j
+    // 4 lanes per symbol, lane j computes bins j + 1 and j + 5 (the 21 erff of a row are the latency of this phase; with 8 lanes
+    // per symbol a full slab needed two passes over the grid's threads), lane 0 gathers, fixes up and stores the packed row
+    const int total = ((len * 4 + 31) >> 5) << 5;  // whole warps
     for (int gt = blockIdx.x * nt + tid; gt < total; gt += (int)gridDim.x * nt) {
-        const int li = gt >> 3, j = gt & 7;
+        const int li = gt >> 2, j = gt & 3;
         const bool live = li < len;
-        float bin = 0.f;
+        float bin_a = 0.f, bin_b = 0.f;
         int th = 0, tw = 0, tc = 0;
         if (live) {
             th = __ldg(net.idx + start + li); tw = __ldg(net.idx + start + li + HW);
@@ -571,27 +573,30 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
                 mv[i] = __ldcg(y + wf_fc_index(net.Dp, net.Hp, G, 3, 2, th + tw, tc, th) + i);
             }
             gmm_prep(wv, dv, 3, 1e-6f);
-            if (j >= 1) bin = gmm_bin_value(wv, dv, mv, j, 3, 3.5f, 65536.f, rows.s2);
+            bin_a = gmm_bin_value(wv, dv, mv, j + 1, 3, 3.5f, 65536.f, rows.s2);
+            if (j < 3) bin_b = gmm_bin_value(wv, dv, mv, j + 5, 3, 3.5f, 65536.f, rows.s2);
         }
         float o[9];
         o[0] = 0.f; o[8] = 65536.f;
+        const int base = tid & 28;
 #pragma unroll
-        for (int k = 1; k < 8; k++) o[k] = __shfl_sync(0xffffffffu, bin, (tid & 24) + k);
+        for (int k = 0; k < 4; k++) {
+            o[1 + k] = __shfl_sync(0xffffffffu, bin_a, base + k);
+            if (k < 3) o[5 + k] = __shfl_sync(0xffffffffu, bin_b, base + k);
+        }
         if (live && j == 0) {
             fixup_row(o, 8, true);
             const int lvl = (int)(rows.levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
             pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows.rows + (size_t)li * 8);
         }
     }
+    // every CTA raises its own host flag once its rows are on their way (the host waits for all of them): no second
+    // device-wide counter round and no second system fence between the last row and the flag
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
-        if (atomicAdd(rows.done, 1) == (int)gridDim.x - 1) {
-            *rows.done = 0;
-            __threadfence_system();
-            *reinterpret_cast<volatile int*>(rows.flag) = psum + 1;
-            WF_TRACE_MAX(net.G, psum, WF_TR_ROWS1);
-        }
+        reinterpret_cast<volatile int*>(rows.flag)[blockIdx.x] = psum + 1;
+        WF_TRACE_MAX(net.G, psum, WF_TR_ROWS1);
     }
 }
 
