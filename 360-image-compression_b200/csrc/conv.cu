@@ -36,7 +36,8 @@ namespace lic360 {
 constexpr int TH = 8, TW = 32, XH = TH + 4, XW = TW + 4;  // EC spatial tile and its halo'd smem tile
 constexpr int EC_CHUNKS = 8;                              // 8 four-channel output chunks (32 channels) per EC block
 constexpr int EC_THREADS = 256;
-constexpr int EC_SMEM_BYTES = (CB * XH * XW + EC_CHUNKS * CB * TAPS * 4) * (int)sizeof(float);
+constexpr int EC_SB = 8;                                  // input channels per pipeline stage (two stages = one canonical block)
+constexpr int EC_SMEM_BYTES = 2 * (EC_SB * XH * XW + EC_CHUNKS * EC_SB * TAPS * 4) * (int)sizeof(float);
 
 // ---------------------------------------------------------------------------------------------------------
 // weight packing: W (nsets,Cout,Cin,5,5) -> Wp [set][chunk][ci][tap][4] ("old" terms, everything else zeroed) and
@@ -111,8 +112,8 @@ __device__ __forceinline__ void ec_taps_fma(const float* xr, const float4* wA, c
 
 __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs a, int pair) {
     extern __shared__ float4 smem_f4[];
-    float* xs = reinterpret_cast<float*>(smem_f4);  // [CB][XH][XW]
-    float4* ws4 = smem_f4 + (CB * XH * XW) / 4;     // [EC_CHUNKS][CB][TAPS] float4
+    float* xs = reinterpret_cast<float*>(smem_f4);       // [2][EC_SB][XH][XW]
+    float4* ws4 = smem_f4 + (2 * EC_SB * XH * XW) / 4;   // [2][EC_CHUNKS][EC_SB][TAPS] float4
 
     const int tid = threadIdx.x;
     const int tx = tid & 7, ty = (tid >> 3) & 7, tz = tid >> 6;
@@ -145,39 +146,61 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
 #pragma unroll
             for (int q = 0; q < 4; q++) P[c][p][q] = 0.f;
 
+    // K loop: 8-channel stages, double buffered with cp.async (the x tile with its halo, zero-filled outside the image, and the
+    // masked weight tile of the 8 chunks land while the previous stage is being consumed); two stages = one canonical 16-channel
+    // block, whose partial sum u is added to P when it is complete.
     const float4* wp4 = reinterpret_cast<const float4*>(a.wp);
-    for (int j = 0; j < nj; j++) {
-        const int cb = min(CB, Cin - j * CB);
-        for (int e = tid; e < cb * XH * XW; e += EC_THREADS) {
-            int ci = e / (XH * XW), r = (e % (XH * XW)) / XW, c = e % XW;
-            int h = h0 + r - 2, w = w0 + c - 2;
-            float v = 0.f;
-            if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(a.x + (((size_t)n * Cin + j * CB + ci) * H + h) * W + w);
-            xs[e] = v;
+    const int nstage = (lim_tile + EC_SB - 1) / EC_SB;
+    (void)nj;
+    const unsigned xs_s = (unsigned)__cvta_generic_to_shared(xs), ws_s = (unsigned)__cvta_generic_to_shared(ws4);
+    auto issue = [&](int st) {
+        const int buf = st & 1, cb8 = min(EC_SB, Cin - st * EC_SB);
+        const unsigned xd = xs_s + (unsigned)buf * (EC_SB * XH * XW * 4), wd = ws_s + (unsigned)buf * (EC_CHUNKS * EC_SB * TAPS * 16);
+        for (int e = tid; e < cb8 * XH * XW; e += EC_THREADS) {
+            const int ci = e / (XH * XW), r = (e % (XH * XW)) / XW, c = e % XW;
+            const int h = h0 + r - 2, w = w0 + c - 2;
+            const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+            cp_async4(xd + 4u * e, ok ? a.x + (((size_t)n * Cin + st * EC_SB + ci) * H + h) * W + w : a.x, ok);
         }
-        for (int e = tid; e < EC_CHUNKS * cb * TAPS; e += EC_THREADS) {
-            int ch = e / (cb * TAPS), r = e % (cb * TAPS);
-            int chunk = chunk0 + ch;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (chunk < a.nchunk) v = __ldg(wp4 + (((size_t)set * a.nchunk + chunk) * Cin + j * CB) * TAPS + r);
-            ws4[ch * CB * TAPS + r] = v;
+        for (int e = tid; e < EC_CHUNKS * cb8 * TAPS; e += EC_THREADS) {
+            const int ch = e / (cb8 * TAPS), r = e % (cb8 * TAPS);
+            const int chunk = chunk0 + ch;
+            const bool ok = chunk < a.nchunk;
+            cp_async16z(wd + 16u * (ch * EC_SB * TAPS + r), ok ? wp4 + (((size_t)set * a.nchunk + chunk) * Cin + st * EC_SB) * TAPS + r : wp4, ok);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    float4 u[2][4];
+    if (nstage > 0) issue(0);
+    for (int st = 0; st < nstage; st++) {
+        if (st + 1 < nstage) {
+            issue(st + 1);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         __syncthreads();
-        if (j * CB < my_lim) {  // warp-uniform: tz is constant inside a warp
-            float4 u[2][4];
+        const int j = st >> 1;             // canonical 16-channel block
+        const bool mine = j * CB < my_lim;  // warp-uniform: tz is constant inside a warp
+        if ((st & 1) == 0) {
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
                 for (int p = 0; p < 4; p++) u[c][p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            // old taps of input group g for output group g_out: kh + kw <= g_out + 2 - g; beyond smax both chunks of
-            // this thread carry zero weights (warp-uniform skip; a single-group net keeps 6 of its 25 taps)
+        }
+        if (mine) {
+            // old taps of input group g for output group g_out: kh + kw <= g_out + 2 - g; beyond that both chunks of this thread
+            // carry zero weights (warp-uniform skip; a single-group net keeps 6 of its 25 taps)
+            const int buf = st & 1, cb8 = min(EC_SB, Cin - st * EC_SB);
+            const float* xb = xs + buf * (EC_SB * XH * XW);
+            const float4* wb = ws4 + buf * (EC_CHUNKS * EC_SB * TAPS);
             const int gmax_out = min(cA + 1, a.nchunk - 1) / a.cpg4;
 #pragma unroll 1
-            for (int ci = 0; ci < cb; ci++) {
-                const float4* wA = ws4 + ((2 * tz) * CB + ci) * TAPS;
-                const float4* wB = ws4 + ((2 * tz + 1) * CB + ci) * TAPS;
-                const float* xr = xs + (ci * XH + ty) * XW + 4 * tx;
-                const int ns = gmax_out + 3 - (j * CB + ci) / a.cin_g;  // taps with kh + kw < ns (warp-uniform)
+            for (int ci = 0; ci < cb8; ci++) {
+                const float4* wA = wb + ((2 * tz) * EC_SB + ci) * TAPS;
+                const float4* wB = wb + ((2 * tz + 1) * EC_SB + ci) * TAPS;
+                const float* xr = xb + (ci * XH + ty) * XW + 4 * tx;
+                const int ns = gmax_out + 3 - (st * EC_SB + ci) / a.cin_g;  // taps with kh + kw < ns (warp-uniform)
                 if (ns >= 9) { ec_taps_fma<9>(xr, wA, wB, u); continue; }  // the common case: straight-line, no tap tests
                 switch (ns) {
                     case 8: ec_taps_fma<8>(xr, wA, wB, u); break;
@@ -191,17 +214,19 @@ __global__ void __launch_bounds__(EC_THREADS, 2) cconv_ec_kernel(const ConvArgs 
                     default: break;
                 }
             }
+            if ((st & 1) == 1 || st + 1 == nstage) {  // the canonical block is complete
 #pragma unroll
-            for (int c = 0; c < 2; c++)
+                for (int c = 0; c < 2; c++)
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    P[c][p][0] = P[c][p][0] + u[c][p].x;
-                    P[c][p][1] = P[c][p][1] + u[c][p].y;
-                    P[c][p][2] = P[c][p][2] + u[c][p].z;
-                    P[c][p][3] = P[c][p][3] + u[c][p].w;
-                }
+                    for (int p = 0; p < 4; p++) {
+                        P[c][p][0] = P[c][p][0] + u[c][p].x;
+                        P[c][p][1] = P[c][p][1] + u[c][p].y;
+                        P[c][p][2] = P[c][p][2] + u[c][p].z;
+                        P[c][p][3] = P[c][p][3] + u[c][p].w;
+                    }
+            }
         }
-        __syncthreads();
+        __syncthreads();  // everyone is done with this buffer before the stage after next lands in it
     }
 
     // P of every output goes to `out`; cconv_ec_rq_kernel adds the R / Q terms and the epilogue in place

@@ -18,6 +18,10 @@ __device__ __forceinline__ void cp_async4(unsigned dst, const void* src, bool va
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
+// 16-byte copy, zero-filled when !valid (src must still be a valid address)
+__device__ __forceinline__ void cp_async16z(unsigned dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0));
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
