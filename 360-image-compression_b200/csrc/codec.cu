@@ -431,19 +431,19 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     LIC360_CUDA(wf_launch_chain(n.wf, s, fused_rows ? &rows : nullptr));
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
-    cudaStream_t rs = s;  // stream of the rows kernel
-    if (fork && rtail) {
-        LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
-        LIC360_CUDA(wf_launch_old(n.wf, 1, s, true));  // programmatic dependent of the chain kernel, see below
-    } else if (fork) {
-        // The old terms of step p+1 only read wavefronts <= p-1: they are launched right behind the chain kernel as its
-        // PROGRAMMATIC dependent -- they start once every chain CTA is resident (so the chain's clusters got their SMs
-        // first) and fill the SMs the chain leaves idle.  The rows kernel needs the chain's RESULTS, so it waits for the
-        // chain's completion on the side stream; both branches join before the step counter advances.
+    // The old terms of step p+1 only read wavefronts <= p-1: they are launched right behind the chain kernel as its
+    // PROGRAMMATIC dependent -- they start once every chain CTA is resident (so the chain's clusters got their SMs first)
+    // and fill the SMs the chain leaves idle.  Whatever still needs the chain's RESULTS (a separate rows kernel, the
+    // previous-wavefront kernel of the next step) waits for the chain's completion on the side stream; when the chain kernel
+    // does all of that itself (rtail) there is no side branch at all.
+    cudaStream_t rs = s;  // stream of the kernels behind the chain
+    if (fork) {
         LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
         LIC360_CUDA(wf_launch_old(n.wf, 1, s, true));
-        LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
-        rs = side;
+        if (!rtail) {
+            LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
+            rs = side;
+        }
     }
     if (fused_rows) {
     } else if (is_code)
@@ -461,7 +461,7 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     WF_DEBUG_SYNC("previous-wavefront kernel (layers 1..11 of the next step)");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[4], s));
     if (fork && rtail) {
-        // the old-term kernel is only a PROGRAMMATIC dependent of the chain: make the step counter wait for the chain itself too
+        // the old-term kernel is only a PROGRAMMATIC dependent of the chain: give the end of the step a full edge from the chain too
         LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_fork, 0));
     } else if (fork) {
         LIC360_CUDA(cudaEventRecord(n.ev_join, side));
