@@ -337,77 +337,6 @@ __global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq_kernel(const ConvAr
     rq_epilogue(a, n, set, chunk, g_out, pos, RQ[0], RQ[1]);
 }
 
-// cin_g == 4 (the code nets): RQ_NP positions per thread, strided by the CTA size so that every activation load stays coalesced.
-// The kernel is bound by the LSU pipe (per position, tap and channel one 4-byte activation load and one broadcast 16-byte weight
-// load, which costs two shared-memory wavefronts, for 4 FMAs): sharing each weight vector between RQ_NP positions removes most of
-// those wavefronts.  Taps outside the image multiply an exact zero instead of being skipped (identical bits, header of this file).
-constexpr int RQ_NP = 4;
-__global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq4_kernel(const ConvArgs a) {
-    extern __shared__ float4 rq_wsm[];  // [2 classes][TAPS][4]
-    const int chunk = blockIdx.y, n = blockIdx.z, set = n / a.per;
-    const int g_out = chunk / a.cpg4;
-    const int H = a.H, W = a.W, HW = a.H * a.W;
-    constexpr int row_f4 = TAPS * 4;
-    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * row_f4;  // float4 per class
-    const float4* wq4 = reinterpret_cast<const float4*>(a.wq) + ((size_t)set * a.nchunk + chunk) * row_f4;
-    const int ncls = a.has_q ? 2 : 1;
-    for (int e = threadIdx.x; e < ncls * row_f4; e += RQ_THREADS) rq_wsm[e] = __ldg(wq4 + (e / row_f4) * wq_cls + e % row_f4);
-    __syncthreads();
-    const int pos0 = blockIdx.x * (RQ_NP * RQ_THREADS) + threadIdx.x;
-    int hh[RQ_NP], ww[RQ_NP];
-#pragma unroll
-    for (int k = 0; k < RQ_NP; k++) {
-        const int pos = pos0 + k * RQ_THREADS;
-        hh[k] = pos < HW ? pos / W : -100;  // out-of-range positions: every tap test fails, nothing is stored
-        ww[k] = pos < HW ? pos % W : -100;
-    }
-    const float* xn = a.x + (size_t)n * a.Cin * HW;
-    float RQ[RQ_NP][2][4];
-#pragma unroll
-    for (int cls = 0; cls < 2; cls++) {
-        float4 u[RQ_NP];
-#pragma unroll
-        for (int k = 0; k < RQ_NP; k++) u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cls < ncls) {
-            const float4* ws = rq_wsm + cls * row_f4;
-#pragma unroll
-            for (int kh = 0; kh < 5; kh++) {
-#pragma unroll
-                for (int kw = 0; kw < 5; kw++) {
-                    const int gq = g_out + 3 + cls - kh - kw;
-                    if (gq < 0 || gq >= a.G) continue;  // CTA-uniform
-                    const float* xg = xn + (size_t)(gq * 4) * HW;
-                    float xx[RQ_NP][4];
-#pragma unroll
-                    for (int k = 0; k < RQ_NP; k++) {
-                        const int ph = hh[k] + kh - 2, pw = ww[k] + kw - 2;
-                        const bool ok = ph >= 0 && ph < H && pw >= 0 && pw < W;
-                        const float* xp = xg + (ok ? ph * W + pw : 0);
-#pragma unroll
-                        for (int c = 0; c < 4; c++) xx[k][c] = ok ? __ldg(xp + (size_t)c * HW) : 0.f;
-                    }
-                    const float4* wt = ws + (kh * 5 + kw) * 4;
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float4 w4 = wt[c];
-#pragma unroll
-                        for (int k = 0; k < RQ_NP; k++) fma4(u[k], xx[k][c], w4);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RQ_NP; k++) {
-            RQ[k][cls][0] = 0.f + u[k].x; RQ[k][cls][1] = 0.f + u[k].y; RQ[k][cls][2] = 0.f + u[k].z; RQ[k][cls][3] = 0.f + u[k].w;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < RQ_NP; k++) {
-        const int pos = pos0 + k * RQ_THREADS;
-        if (pos < HW) rq_epilogue(a, n, set, chunk, g_out, pos, RQ[k][0], RQ[k][1]);
-    }
-}
-
 __global__ void __launch_bounds__(640, 2) cconv_ec_rqb_kernel(const ConvArgs a, int nqb, int tap_cap) {
     extern __shared__ float4 rq_wsm[];  // [2 classes][tap_cap][cin_g] weights of the taps that select a valid group, then partials
     __shared__ int s_tap[2][TAPS], s_ntap[2];
@@ -648,11 +577,7 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
     if (nqb == 1) {
         const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);  // <= 12.8 KB
         dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);
-        static const bool rq4 = getenv("LIC360_EC_RQ4") != nullptr;  // 4 positions per thread: opt-in until it has been through the GPU suite
-        if (a.cin_g == 4 && rq4) {
-            dim3 grid4((a.H * a.W + RQ_NP * RQ_THREADS - 1) / (RQ_NP * RQ_THREADS), a.nchunk, a.N);
-            cconv_ec_rq4_kernel<<<grid4, RQ_THREADS, rq_smem, s>>>(a);
-        } else if (a.cin_g == 4) cconv_ec_rq_kernel<4><<<grid2, RQ_THREADS, rq_smem, s>>>(a);
+        if (a.cin_g == 4) cconv_ec_rq_kernel<4><<<grid2, RQ_THREADS, rq_smem, s>>>(a);
         else cconv_ec_rq_kernel<0><<<grid2, RQ_THREADS, rq_smem, s>>>(a);
     } else {
         if (2 * nqb > 20) return cudaErrorInvalidConfiguration;  // cin_g <= 160

@@ -295,7 +295,10 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic_note": prof.get("note"), "traffic_step_algorithmic_bytes": prof.get("algorithmic_bytes_this_step"),
                 "kernel_ms_per_decode": {"code": kt, "importance": kt_imp},
-                "note": "avg launch = CUDA-event time around every wf_old_kernel launch of one serialized decode on the codec stream (DESIGN.md s5)"}
+                "shares_under_ncu": prof.get("shares_of_summed_gpu_time_under_ncu"),
+                "note": "avg launch = CUDA-event time around every wf_old_kernel launch of one serialized decode on the codec stream (DESIGN.md s5). "
+                        "wf_old_kernel is the kernel that moves the data and occupies the whole GPU; the chain kernels (chain_ms: 24 resp. 16 SMs, "
+                        "cluster barriers, incl. the fused CDF rows and next-step R terms) are latency-bound and have no bandwidth roofline"}
     line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
