@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
 // activation reads (row stride cin_g + 4) feeds kpc independent accumulator chains, weights are broadcasts.
 constexpr int C1_KB = 3;  // chunks a warp accumulates together
 __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant__ WfNetDev net, int nc, int kpc, int lenp,
-                                                         int cmax, WfRows rows, int r0_inline) {
+                                                         int cmax, WfRows rows, int r0_inline, int dsm) {
     extern __shared__ float4 wf_sm1[];
     __shared__ unsigned long long wbar_mem;  // mbarrier of the weight staging
     cg::cluster_group cluster = cg::this_cluster();
@@ -790,9 +790,14 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
     const int xs = cmax + 4;                                            // padded row stride of the activation tile (floats)
     const int xt_floats = (lenp + 4) * xs;
     float4* wbuf = wf_sm1;                                              // [2][kpc][5][cmax] float4
-    float* xt = reinterpret_cast<float*>(wbuf + (size_t)2 * kpc * 5 * cmax);   // [2][lenp + 4][xs]: input tile of layer l in half l & 1
-    float4* part = reinterpret_cast<float4*>(xt + (size_t)2 * xt_floats);     // [kpc][nqb_max][lenp]
-    float* ylog = reinterpret_cast<float*>(part + (size_t)kpc * nqb_max * lenp);  // [lenp][52]: last layer's logits, gathered in CTA 0
+    // dsm: input tile of layer l in half l & 1, filled by the previous layer's epilogues through distributed shared memory.
+    // !dsm (diagonals too long for two tiles): one tile, reloaded from the L2-resident frame behind every cluster barrier.
+    float* xt = reinterpret_cast<float*>(wbuf + (size_t)2 * kpc * 5 * cmax);   // [dsm ? 2 : 1][lenp + 4][xs]
+    float4* part = reinterpret_cast<float4*>(xt + (size_t)(dsm ? 2 : 1) * xt_floats);  // [kpc][nqb_max][lenp]
+    // [lenp][52]: the last layer's logits, gathered in CTA 0.  They live in weight buffer 0, which is idle by then: the last layer
+    // (odd) computes out of buffer 1 and nothing is staged after it (host side checks that the buffer is large enough)
+    static_assert(((WF_LAYERS - 1) & 1) == 1, "the logits reuse weight buffer 0 during the last layer");
+    float* ylog = reinterpret_cast<float*>(wbuf);
     const unsigned wbar = (unsigned)__cvta_generic_to_shared(&wbar_mem);
     if (tid == 0) {
         mbar_init(wbar, 1);
@@ -801,7 +806,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
     __syncthreads();
     // rows hmin-2, hmin-1, hmin+len, hmin+len+1 of the diagonal are outside the image (or outside the frame's written part): zero;
     // rows 2 .. len+1 are completely rewritten by the producers of every layer
-    for (int e = tid; e < 2 * 4 * xs; e += nt) {
+    for (int e = tid; e < (dsm ? 2 : 1) * 4 * xs; e += nt) {
         const int half = e / (4 * xs), r4 = (e / xs) % 4, c = e % xs;
         xt[(size_t)half * xt_floats + (size_t)(r4 < 2 ? r4 : len + r4) * xs + c] = 0.f;
     }
@@ -874,7 +879,16 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
         phase(l, 0);
         if (L.has_q && kn > 0) {
             const int cg = L.cin_g;
-            const float* xl = xt + (size_t)(l & 1) * xt_floats;  // rows hmin-2 .. hmin+len+1, stored by the previous layer's epilogues
+            const float* xl = xt + (size_t)(dsm ? (l & 1) : 0) * xt_floats;  // rows hmin-2 .. hmin+len+1 of the diagonal
+            if (!dsm) {  // one contiguous block of the channel-last frame, written by all CTAs of the cluster before the barrier
+                const float4* xsrc = reinterpret_cast<const float4*>(L.xc + wf_fc_index(net.Dp, net.Hp, 1, cg, n, d, 0, hmin - 2));
+                const int row_f4 = cg >> 2;
+                for (int e = tid; e < (len + 4) * row_f4; e += nt) {
+                    const int r = e / row_f4, c4 = e % row_f4;
+                    *reinterpret_cast<float4*>(xt + (size_t)r * xs + 4 * c4) = __ldcg(xsrc + e);
+                }
+                __syncthreads();
+            }
             const float4* wl = wbuf + (size_t)(l & 1) * kpc * 5 * cmax;
             const int npg = (len + 31) >> 5, nqb = L.nqb;
             for (int k0 = 0; k0 < kn; k0 += C1_KB) {
@@ -914,7 +928,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
         }
         phase(l, 1);
         // ranks that consume this layer's output in the next layer (those that own output chunks there)
-        const int nranks_next = (l + 1 < WF_LAYERS && net.L[l + 1].has_q) ? min(nc, (net.L[l + 1].cpg4 + kpc - 1) / kpc) : 0;
+        const int nranks_next = (dsm && l + 1 < WF_LAYERS && net.L[l + 1].has_q) ? min(nc, (net.L[l + 1].cpg4 + kpc - 1) / kpc) : 0;
         float* xnext = xt + (size_t)((l + 1) & 1) * xt_floats;
         for (int it = tid; it < kn * len; it += nt) {
             const int k = it / len, pos = it % len, kc = kc0 + k, h = hmin + pos;
@@ -1127,9 +1141,14 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         if (e.chain1) {
             e.c1_kpc = (e.cpg4_max + e.cluster - 1) / e.cluster;
             e.c1_lenp = ((max_len + 31) / 32) * 32;
-            const size_t sm = (size_t)2 * e.c1_kpc * 5 * e.c1_cmax * sizeof(float4) + (size_t)2 * (e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float) +
-                              (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4) + (size_t)e.c1_lenp * 52 * sizeof(float);
-            if (sm <= 200 * 1024) { e.chain_smem = sm; e.chain_threads = 384; }
+            const size_t wbuf1 = (size_t)e.c1_kpc * 5 * e.c1_cmax * sizeof(float4);                  // one weight buffer
+            const size_t tile = (size_t)(e.c1_lenp + 4) * (e.c1_cmax + 4) * sizeof(float);            // one activation tile
+            const size_t parts = (size_t)e.c1_kpc * ((e.c1_cmax + CB - 1) / CB) * e.c1_lenp * sizeof(float4);
+            const bool logits_fit = (size_t)e.c1_lenp * 52 * sizeof(float) <= wbuf1;                 // they reuse weight buffer 0
+            const size_t cap = 226 * 1024;  // 227 KB per CTA minus the kernel's static shared memory
+            e.c1_dsm = logits_fit && 2 * wbuf1 + 2 * tile + parts <= cap;   // activations exchanged through distributed shared memory
+            const size_t sm = 2 * wbuf1 + (e.c1_dsm ? 2 : 1) * tile + parts;
+            if (logits_fit && sm <= cap) { e.chain_smem = sm; e.chain_threads = 384; }
             else e.chain1 = false;  // too large for shared memory: the generic chain kernel handles it
         }
         if (e.chain_smem > 200 * 1024) { set_error("wavefront engine: slab too large for the chain kernel"); return LIC360_ERR_ARG; }
@@ -1238,7 +1257,7 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* row
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
     if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r, (int)(e.r0_inline && r.enabled));
-    if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax, r, (int)(e.r0_inline && r.enabled));
+    if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax, r, (int)(e.r0_inline && r.enabled), (int)e.c1_dsm);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }
 

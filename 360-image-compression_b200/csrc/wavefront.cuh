@@ -68,6 +68,7 @@ struct WfEngine {
     int cluster = 1, chain_threads = 0;
     bool chain4 = false;  // every chained layer has 4 channels per group: the staged-weight chain kernel applies
     bool chain1 = false;  // single-group net: the output-chunk-split chain kernel applies
+    bool c1_dsm = false;  // chain1: both activation tiles fit, layers exchange activations through distributed shared memory
     bool r0_inline = false;  // the chain kernel computes layer 0's previous-wavefront terms itself (no launch for them)
     int c1_kpc = 0, c1_lenp = 0, c1_cmax = 0, prev_wcap = 0;
     size_t old_smem = 0, prev_smem = 0, chain_smem = 0;

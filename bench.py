@@ -150,6 +150,11 @@ def main():
         # reference arm: the CPU implementation of the path on the host cores; rank 0 alone runs it
         if rank != 0:
             return
+        # torchrun exports OMP_NUM_THREADS=1 to every worker unless the user set it; this arm is meant to use all host threads
+        # (the variable has to be right before libgomp / torch are loaded, which happens inside cpu_arm)
+        if world > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
+            if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+                os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
         steps = max(1, min(args.steps, 3))
         cb, t = cpu_arm(steps, min(args.warmup, 1))
         line = {"impl": "reference", "metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": cb["value"], "unit": "Mpx/s",
