@@ -505,7 +505,7 @@ static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
             // code stream: critical kernels highest, its old-term kernel lowest; the importance stream has slack (it only has
             // to stay ahead of the code stream): one level below the code stream's critical kernels, old terms lowest
             const int hi = is_code ? prio_hi : std::min(prio_lo, prio_hi + 2);
-            v.priority = kp.func == wf_old_kernel_ptr() ? prio_lo : hi;
+            v.priority = (kp.func == wf_old_kernel_ptr() || kp.func == wf_old2_kernel_ptr()) ? prio_lo : hi;
             cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v);
         }
         cudaGetLastError();

@@ -166,6 +166,92 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
     if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(net.G, t.psum - dp, WF_TR_OLD1);
 }
 
+// ------------------------------------------------------------------------------------------------ old terms, 2 positions / lane
+// Same tile decomposition as wf_old_kernel but a CTA covers 64 consecutive positions of the diagonal and every lane owns two
+// ADJACENT ones (dc_taps_fma2): the tile starts at the even position below hmin so that the float2 band reads are aligned, the
+// TMA box is {72 h, 9 d, 2 c} starting at the multiple of 4 below (tile start - 2).  Two channels per stage: the same bytes,
+// MACs and shared memory per stage (hence the same 6 CTAs per SM) as the one-position kernel's 4-channel stage over 32
+// positions, with 176 instead of 300 shared-memory load wavefronts.
+constexpr int WF2_STAGE = 2;
+constexpr int WF2_BOX_W = 72;
+constexpr int WF2_BAND = 9 * WF2_BOX_W;
+constexpr int WF2_BAND_BYTES = WF2_STAGE * WF2_BAND * 4;
+constexpr int WF2_STAGE_BYTES = ((WF2_BAND_BYTES + WF2_STAGE * TAPS * 16 + 127) / 128) * 128;
+
+__global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old2_kernel(const __grid_constant__ WfNetDev net,
+                                                                   const __grid_constant__ WfMaps maps, int dp, int l0, int parts2) {
+    extern __shared__ unsigned char wf_raw[];
+    // grid = ((layer, net), chunk, (diagonal, part)), x fastest: the heaviest output groups of every layer start first
+    const int bx = blockIdx.z, bz = blockIdx.x;
+    const int l = l0 + bz / net.nsets, n = bz % net.nsets, kc = blockIdx.y;
+    const int psum = *net.ctr + dp;
+    if (kc >= net.L[l].cpg4 || psum >= net.nsteps) return;
+    const int la = max(0, psum - net.G + 1), lb = min(psum, net.H + net.W - 2);
+    const int d = la + bx / parts2;
+    if (d > lb) return;
+    const int hmin = max(0, d - net.W + 1), hmax = min(net.H - 1, d);
+    const int hb = (hmin & ~1) + (bx % parts2) * 64;   // even: the lane's pair (hb + 2 lane, hb + 2 lane + 1) is float2-aligned
+    if (hb > hmax) return;                             // CTA-uniform
+    const int tc = psum - d;
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(net.G, psum - dp, WF_TR_OLD0);
+    const WfLayerDev& L = net.L[l];
+    const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
+    unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
+    float4* part = reinterpret_cast<float4*>(base + (size_t)WF_OLD_WARPS * WF2_STAGE_BYTES);   // [nblk][64]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + L.nblk * 64);      // [WF_OLD_WARPS]
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    float* band = reinterpret_cast<float*>(base + (size_t)seg * WF2_STAGE_BYTES);
+    float4* wsm = reinterpret_cast<float4*>(band + WF2_STAGE * WF2_BAND);
+    const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
+    const unsigned wsm_s = band_s + WF2_BAND_BYTES;
+    const int h0 = (hb - 2) & ~3;          // aligned box start (also for negative values: two's complement floor)
+    const float* bandl = band + (hb - 2 - h0);   // 0 or 2 floats in
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + seg);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int Cin = L.Cin;
+    const int lim = min(Cin, (tc + 3) * L.cin_g);  // old terms: g_in <= tc + 2
+    const int nact = (lim + CB - 1) / CB;          // canonical blocks that have old terms
+    const int chunk = tc * L.cpg4 + kc;
+    unsigned phase = 0;
+    for (int j = seg; j < nact; j += WF_OLD_WARPS) {
+        float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+        const int cb = min(CB, Cin - j * CB);
+        const float4* wp4 = reinterpret_cast<const float4*>(L.wp) + (((size_t)n * L.nchunk + chunk) * Cin + j * CB) * TAPS;
+        for (int c0 = 0; c0 < cb && j * CB + c0 < lim; c0 += WF2_STAGE) {
+            const int nc = min(WF2_STAGE, cb - c0);
+            __syncwarp();  // every lane is done with the previous stage
+            if (lane == 0) {
+                mbar_expect_tx(bar, WF2_BAND_BYTES + nc * TAPS * 16);
+                tma_load_3d(band_s, &maps.tm[l], h0, d - 4, n * Cin + j * CB + c0, bar);
+                bulk_load(wsm_s, wp4 + c0 * TAPS, nc * TAPS * 16, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            dc_stage_fma2<WF2_BOX_W, WF2_BAND>(bandl, wsm, nc, lane, j * CB + c0, L.cin_g, tc, u0, u1);
+        }
+        part[j * 64 + 2 * lane] = u0;
+        part[j * 64 + 2 * lane + 1] = u1;
+    }
+    __syncthreads();
+    // the block sums in canonical order: warp 0 finishes the even positions, warp 1 the odd ones
+    if (seg < 2) {
+        const int pos = 2 * lane + seg, h = hb + pos;
+        if (h >= hmin && h <= hmax) {
+            float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < nact; j++) {  // blocks without old terms add nothing (the encoder skips them too)
+                const float4 v = part[j * 64 + pos];
+                P.x = P.x + v.x; P.y = P.y + v.y; P.z = P.z + v.z; P.w = P.w + v.w;
+            }
+            L.pbuf[psum & 1][(((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h] = P;
+        }
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(net.G, psum - dp, WF_TR_OLD1);
+}
+
 // ------------------------------------------------------------------------------------------------ R / Q terms
 // one canonical 16-channel block (jq) of the previous-wavefront (cls 0) or same-wavefront (cls 1) terms of output
 // (d, h, group tc, chunk kc): every tap reads the cin_g channels of ONE input group from the channel-last frame.
@@ -1087,15 +1173,26 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     for (int l = 0; l < WF_LAYERS; l++) {
         const cuuint64_t dims[3] = {(cuuint64_t)n.HS, (cuuint64_t)n.D, (cuuint64_t)nsets * e.C[l]};
         const cuuint64_t strides[2] = {(cuuint64_t)n.HS * 4, (cuuint64_t)n.D * n.HS * 4};
-        const cuuint32_t box[3] = {WF_BOX_W, 9, WF_STAGE};
+        const cuuint32_t box[3] = {WF_BOX_W, 9, WF_STAGE}, box2[3] = {WF2_BOX_W, 9, WF2_STAGE};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&e.maps.tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e.fp[l], dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
+        r = enc(&e.maps2.tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e.fp[l], dims, strides, box2, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled (72-wide box) failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
     }
     // launch shapes
     e.old_smem = 128 + (size_t)WF_OLD_WARPS * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
+    // two positions per lane for the many-group nets (LIC360_WF_OLD1=1: the one-position kernel).  The single-group net keeps the
+    // one-position kernel: its diagonals are short (half-empty warps) and its old-term launch is latency-, not throughput-critical
+    // (twice as many TMA round trips per warp made the importance stream gate the code stream at 2048x4096).
+    e.old2 = G > 1 && getenv("LIC360_WF_OLD1") == nullptr;
+    // a diagonal with an odd first row starts its tile one position early; only when H > W can such a diagonal have full length
+    e.parts2 = (std::min(H, W) + (H > W ? 1 : 0) + 63) / 64;
+    e.old2_smem = 128 + (size_t)WF_OLD_WARPS * WF2_STAGE_BYTES + (size_t)e.nblk_max * 64 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
     e.prev_wcap = 0;
     for (int l = 0; l < WF_LAYERS; l++) e.prev_wcap = std::max(e.prev_wcap, TAPS * n.L[l].cin_g);
     e.prev_smem = ((size_t)e.prev_wcap + (size_t)e.nqb_max * 32) * sizeof(float4);
@@ -1110,6 +1207,11 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     if (e.old_smem > old_attr) {
         LIC360_CUDA(cudaFuncSetAttribute(wf_old_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old_smem));
         old_attr = e.old_smem;
+    }
+    static size_t old2_attr = 48 * 1024;
+    if (e.old2_smem > old2_attr) {
+        LIC360_CUDA(cudaFuncSetAttribute(wf_old2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old2_smem));
+        old2_attr = e.old2_smem;
     }
     // chain kernels: one cluster per net.  16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
     // else the portable maximum of 8.
@@ -1181,6 +1283,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
 }
 
 const void* wf_old_kernel_ptr() { return reinterpret_cast<const void*>(&wf_old_kernel); }
+const void* wf_old2_kernel_ptr() { return reinterpret_cast<const void*>(&wf_old2_kernel); }
 
 void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope) {
     WfLayerDev& L = e.dev.L[l];
@@ -1207,7 +1310,7 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(32, WF_OLD_WARPS);
-    cfg.dynamicSmemBytes = e.old_smem;
+    cfg.dynamicSmemBytes = e.old2 ? e.old2_smem : e.old_smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start once the previous kernel's CTAs have all
@@ -1219,10 +1322,11 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     const int split = n.G > 1 ? split_env : 1;
     for (int k = 0; k < split; k++) {
         const int l0 = k * WF_LAYERS / split, l1 = (k + 1) * WF_LAYERS / split;
-        cfg.gridDim = dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * n.parts);
+        cfg.gridDim = dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * (e.old2 ? e.parts2 : n.parts));
         cfg.numAttrs = programmatic && k == 0 ? 1 : 0;
         g_launches++;
-        const cudaError_t err = cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
+        const cudaError_t err = e.old2 ? cudaLaunchKernelEx(&cfg, wf_old2_kernel, n, e.maps2, dp, l0, e.parts2)
+                                       : cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
         if (err != cudaSuccess) return err;
     }
     return cudaSuccess;

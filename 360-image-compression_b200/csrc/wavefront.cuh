@@ -58,6 +58,10 @@ struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer,
 struct WfEngine {
     WfNetDev dev;
     WfMaps maps;
+    WfMaps maps2;         // box {72 h, 9 d, 2 c} of the two-positions-per-lane old-term kernel
+    bool old2 = false;    // use it (many-group nets; LIC360_WF_OLD1=1 switches back)
+    int parts2 = 1;       // 64-position parts per diagonal
+    size_t old2_smem = 0;
     float* fp[WF_LAYERS + 1] = {nullptr};
     float* fc[WF_LAYERS + 1] = {nullptr};
     size_t fp_floats[WF_LAYERS + 1] = {0}, fc_floats[WF_LAYERS + 1] = {0};
@@ -79,7 +83,8 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
             const int* ctr_dev, int nsteps, int max_len);
 void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope);
 void wf_free(WfEngine& e);
-const void* wf_old_kernel_ptr();  // to give the old-term kernel node its own (lowest) priority in the step graph
+const void* wf_old_kernel_ptr();
+const void* wf_old2_kernel_ptr();  // to give the old-term kernel node its own (lowest) priority in the step graph
 cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)
 // P of step *ctr + dp, all layers.  programmatic: launch as a programmatic dependent of the previous kernel in the stream
 cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic = false);
