@@ -955,6 +955,14 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
             for (int k = 1; k < WF_TR_SLOTS; k++) fprintf(stderr, " %s +%.1f;", names[k], acc[k] / cnt);
             fprintf(stderr, "\n");
         }
+        if (!tr_sel) {
+            fprintf(stderr, "lic360 trace, code-stream chain, CTA 0 thread 0, us per layer [weight staging issue | item: 25 loads, 100 FMA4, stores | prefetch issue + weights landed | cluster barrier]:");
+            for (int l = 0; l < 12; l++) {
+                fprintf(stderr, " L%d", l);
+                for (int ph = 0; ph < 4; ph++) fprintf(stderr, "%c%.2f", ph ? '|' : ' ', (double)tr[(size_t)tr_steps * WF_TR_SLOTS + l * 4 + ph] * 1e-3 / tr_net.nsteps);
+            }
+            fprintf(stderr, "\n");
+        }
         if (tr_sel) {
             fprintf(stderr, "lic360 trace, G=1 chain, CTA 0, us per layer [weight staging | Q product | epilogue + DSMEM stores | prefetch + cluster barrier]:");
             for (int l = 0; l < 12; l++) {

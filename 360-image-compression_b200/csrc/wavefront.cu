@@ -763,6 +763,17 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
         wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
         if (r0_inline) pre.rr = wf_r_layer0_c1(net, n, d0, h0, tc0);  // no launch computed layer 0's R for this step
     }
+    // debug timeline (LIC360_WF_TRACE=1): ns spent by thread 0 of CTA 0 in the phases of every layer, accumulated behind the step slots
+    const bool phase_trace = g_wf_trace && g_wf_trace_sel == 0 && blockIdx.x == 0 && tid == 0;
+    unsigned long long tph = 0;
+    auto phase = [&](int l, int ph) {
+        if (!phase_trace) return;
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        if (ph >= 0) atomicAdd(g_wf_trace + (size_t)(net.nsteps + 2) * WF_TR_SLOTS + l * 4 + ph, t_ - tph);
+        tph = t_;
+    };
+    phase(0, -1);
     for (int l = 0; l < WF_LAYERS; l++) {
         const WfLayerDev& L = net.L[l];
         // stage the same-wavefront weights of the next layer: rows tc_lo .. tc_lo + nrows - 1 are contiguous in wq
@@ -774,6 +785,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
             asm volatile("cp.async.commit_group;\n" ::);
         }
         const float4* wl = wf_wsm + (size_t)(l & 1) * rows_cap * WF_ROW_F4;
+        phase(l, 0);
         for (int il = tid; il < nloc; il += nt) {
             int h = h0, d = d0, tc = tc0;
             WfPre p = pre;
@@ -833,12 +845,15 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                     if (q < L.cout_g) L.oc[fc + q] = v[q];
             }
         }
+        phase(l, 1);
         if (l + 1 < WF_LAYERS) {
             if (has0) wf_chain4_prefetch(net, net.L[l + 1], n, par, d0, h0, tc0, pre);
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            phase(l, 2);
             if (nc > 1) cg::this_cluster().sync();
             else __syncthreads();
         }
+        phase(l, 3);
     }
     if (threadIdx.x == 0) WF_TRACE_MAX(net.G, sd.psum, WF_TR_CHAIN1);
     if (rows.enabled) wf_chain4_rows(net, rows, sd.psum, sd.start, sd.len, tid, nt);

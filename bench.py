@@ -12,7 +12,7 @@ collective on the codec path), so scaling is weak: value = N * 0.
 `value`  : inputs resident in HBM, outputs left in HBM.
 `e2e`    : the same call with the latent in pinned HOST memory: H2D of (code, mask, importance levels) and D2H of the
            decoded (code, mask) inside the timed region.
-`roofline`: dominant kernel = wf_old_kernel (old terms of all 12 context-conv layers of a wavefront step, TMA-fed),
+`roofline`: dominant kernel = wf_old2_kernel (old terms of all 12 context-conv layers of a wavefront step, TMA-fed),
            timed with CUDA events on the codec stream in one extra serialized decode.
 `cpu_baseline` / `--impl reference`: the CPU rendition (oracle/: OpenMP restatement of the conv/table ops + the
            reference's own host arithmetic coder when oracle/_ref is built) on a bounded sample, all host threads.
@@ -294,15 +294,15 @@ def main():
         pass
     old_launch_us = kt["old_ms"] / max(kt["steps"], 1) * 1e3
     achieved = alg_bytes / (old_launch_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "wf_old_kernel (TMA-fed old-term context conv of all 12 layers x 3 nets of a wavefront step, code stream)",
+    roofline = {"bound": "hbm", "kernel": "wf_old2_kernel (TMA-fed old-term context conv of all 12 layers x 3 nets of a wavefront step, code stream; two positions per lane)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": old_launch_us, "launches_per_decode": n_old,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic_note": prof.get("note"), "traffic_step_algorithmic_bytes": prof.get("algorithmic_bytes_this_step"),
                 "kernel_ms_per_decode": {"code": kt, "importance": kt_imp},
                 "shares_under_ncu": prof.get("shares_of_summed_gpu_time_under_ncu"),
-                "note": "avg launch = CUDA-event time around every wf_old_kernel launch of one serialized decode on the codec stream (DESIGN.md s5). "
-                        "wf_old_kernel is the kernel that moves the data and occupies the whole GPU; the chain kernels (chain_ms: 24 resp. 16 SMs, "
+                "note": "avg launch = CUDA-event time around every old-term kernel launch (wf_old2_kernel) of one serialized decode on the codec stream (DESIGN.md s5). "
+                        "the old-term kernel is the kernel that moves the data and occupies the whole GPU; the chain kernels (chain_ms: 24 resp. 16 SMs, "
                         "cluster barriers, incl. the fused CDF rows and next-step R terms) are latency-bound and have no bandwidth roofline"}
     line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
