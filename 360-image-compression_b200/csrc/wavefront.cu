@@ -810,6 +810,15 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                 for (int kh = 0; kh < 5; kh++)
 #pragma unroll
                     for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = __ldcg(xr + (kh + kw) * srow + kh);
+#ifdef LIC360_WF_FINE_TRACE
+                if (phase_trace) {  // all 25 loads have landed when their sum is known
+                    float acc = 0.f;
+#pragma unroll
+                    for (int t = 0; t < TAPS; t++) acc += xv[t].x;
+                    if (acc == 123456.789f) u.x = 1.f;
+                    phase(l, 0);
+                }
+#endif
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++)
 #pragma unroll
@@ -822,6 +831,9 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                             fma4(u, xs[c], w4);
                         }
                     }
+#ifdef LIC360_WF_FINE_TRACE
+                if (phase_trace) { if (u.x == 123456.789f) u.y = 1.f; phase(l, 2); }
+#endif
             }
             const float Q[4] = {0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w};  // Q = 0 + q_0 (one canonical block)
             const float PR[4] = {p.pr.x + p.rr.x, p.pr.y + p.rr.y, p.pr.z + p.rr.z, p.pr.w + p.rr.w};
