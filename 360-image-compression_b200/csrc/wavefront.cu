@@ -577,6 +577,12 @@ __global__ void __launch_bounds__(MAXT, 1) wf_chain_kernel(const __grid_constant
 //   - P + R, bias, slope and the residual of layer l+1 are loaded into registers before the barrier that ends layer l,
 //   - the 25 activation loads of an item (one float4 per tap) are all in flight before the first FMA.
 // Per layer that leaves: cluster barrier -> one L2 round trip -> 400 FMAs against shared-memory weights -> stores.
+// tap loads of the code-stream chain: plain loads (see wf_chain4_kernel); -DLIC360_WF_TAPS_CG restores ld.global.cg
+#ifdef LIC360_WF_TAPS_CG
+#define WF_TAP_LOAD(p) __ldcg(p)
+#else
+#define WF_TAP_LOAD(p) (*(p))
+#endif
 constexpr int WF_ROW_F4 = TAPS * 4;  // float4 per (output group) row of same-wavefront weights when cin_g == 4
 
 struct WfPre { float4 pr, rr; float bs[4], sl[4], rs[4]; };  // P and R: added where they are consumed, a layer later
@@ -806,10 +812,13 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                 const size_t srow = (size_t)(GP - 1) * net.Hp;
                 const float4* wr = wl + (size_t)(tc - tc_lo) * WF_ROW_F4;
                 float4 xv[TAPS];
+                // Plain (L1-allocating) loads: the values were stored by CTAs of THIS cluster before the cluster barrier, whose
+                // acquire makes them visible to weak loads as well, and neighbouring positions share most of their 25 taps -- with
+                // ld.global.cg every tap of every lane went to L2 (90 KB per CTA and layer, 1.6 us); through L1 only the first touch does.
 #pragma unroll
                 for (int kh = 0; kh < 5; kh++)
 #pragma unroll
-                    for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = __ldcg(xr + (kh + kw) * srow + kh);
+                    for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = WF_TAP_LOAD(xr + (kh + kw) * srow + kh);
 #ifdef LIC360_WF_FINE_TRACE
                 if (phase_trace) {  // all 25 loads have landed when their sum is known
                     float acc = 0.f;
