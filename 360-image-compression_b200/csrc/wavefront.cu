@@ -716,7 +716,7 @@ __device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int ran
 #pragma unroll
         for (int kh = 0; kh < 5; kh++)
 #pragma unroll
-            for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = __ldcg(xr + (kh + kw) * srow + kh);
+            for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = WF_TAP_LOAD(xr + (kh + kw) * srow + kh);  // this cluster's stores, behind its barriers
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kh = 0; kh < 5; kh++)
