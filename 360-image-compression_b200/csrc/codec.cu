@@ -19,6 +19,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <sched.h>
 #include <thread>
 #include <cmath>
@@ -73,8 +76,75 @@ struct NetDesc {
 
 using namespace lic360;
 
+namespace lic360 {
+// Per-device admission of concurrent decodes: the code-stream chain kernel's three clusters meet at a global
+// counter, which only works while every cluster of every running chain is resident.  A decode takes a slot for its duration;
+// the capacity comes from cudaOccupancyMaxActiveClusters (wf_chain_capacity), further decodes queue here on the host.
+struct ChainSlots {
+    std::mutex m;
+    std::condition_variable cv;
+    int in_use[kMaxDevices] = {0};
+    void acquire(int dev, int cap) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return in_use[dev] < cap; });
+        in_use[dev]++;
+    }
+    void release(int dev) {
+        { std::lock_guard<std::mutex> lk(m); in_use[dev]--; }
+        cv.notify_all();
+    }
+};
+static ChainSlots g_chain_slots;
+struct ChainSlot {
+    int dev;
+    ChainSlot(int d, int cap) : dev(d) { g_chain_slots.acquire(d, cap); }
+    ~ChainSlot() { g_chain_slots.release(dev); }
+};
+
+// the importance stream of a decode runs on a second host thread: one persistent worker per codec (not a std::thread per call)
+struct StreamWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false, busy = false;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<void()> j = std::move(job);
+            has_job = false;
+            lk.unlock();
+            j();
+            lk.lock();
+            busy = false;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> j) {
+        std::unique_lock<std::mutex> lk(m);
+        if (!th.joinable()) th = std::thread([this] { loop(); });
+        job = std::move(j);
+        has_job = true; busy = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return !busy; });
+    }
+    ~StreamWorker() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+}  // namespace lic360
+
 struct lic360_codec {
     int device = 0, H = 0, W = 0;
+    int chain_cap = 1;                  // concurrent decodes the device can hold (wf_chain_capacity)
+    lic360::StreamWorker imp_worker;
     int mode = 0;                       // 0: pipelined graph replay, 1: serialized launches with per-kernel event timing
     NetDesc code, imp;
     float* levels_dev = nullptr;        // decoded importance levels (1,1,H/2,W/2), filled diagonal by diagonal
@@ -137,7 +207,11 @@ __global__ void gmm_rows_kernel(const float* __restrict__ y, const float* __rest
     }
     gmm_row(wv, dv, mv, o, 3, 8, 3.5f, 65536.f, 1e-6f, s2);
     const size_t pos = ((size_t)tc * H + th) * W + tw;
-    const int sym = code ? (int)code[pos] : 0;
+    int sym = 0;
+    if (code) {  // NaN and anything outside [0, 8) become the out-of-range marker of the packed row
+        const float cv = code[pos];
+        sym = (cv >= 0.f && cv < 8.f) ? (int)cv : 8;
+    }
     pack_gmm_row(o, sym, mask[pos] < 0.5f ? 0 : 1, rows + (size_t)row * 8);
 }
 
@@ -561,7 +635,8 @@ static void ctx_free(NetDesc& n) {
 
 lic360_codec* lic360_codec_create(int device, int H, int W) {
     if (H <= 0 || W <= 0 || (H % 2) || (W % 2)) { set_error("codec: latent size must be positive and even"); return nullptr; }
-    if (cudaSetDevice(device) != cudaSuccess) { set_error("codec: cudaSetDevice(%d) failed", device); return nullptr; }
+    DeviceGuard guard(device);  // the caller's current device is restored on return
+    if (guard.err != cudaSuccess) { set_error("codec: cudaSetDevice(%d) failed", device); return nullptr; }
     lic360_codec* c = new lic360_codec();
     c->device = device; c->H = H; c->W = W;
     net_init(c->code, 48, 4, 3, 3, H, W);
@@ -575,6 +650,7 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
     ok = ok && wf_init(c->code.wf, 48, 4, 3, 3, H, W, c->code.idx_dev, c->code.steps_dev, c->code.ctr_dev, c->code.nsteps, c->code.max_len) == LIC360_OK;
     ok = ok && wf_init(c->imp.wf, 1, 144, 49, 1, H / 2, W / 2, c->imp.idx_dev, c->imp.steps_dev, c->imp.ctr_dev, c->imp.nsteps, c->imp.max_len) == LIC360_OK;
     const bool wf_ok = ok || !pre_ok;
+    if (ok) c->chain_cap = wf_chain_capacity(c->code.wf);
     ok = ok && cudaMalloc(&c->levels_dev, (size_t)(H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mask192_dev, (size_t)192 * (H / 2) * (W / 2) * sizeof(float)) == cudaSuccess;
     if (!ok) {
@@ -587,7 +663,7 @@ lic360_codec* lic360_codec_create(int device, int H, int W) {
 
 void lic360_codec_destroy(lic360_codec* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     net_free(c->code); net_free(c->imp);
     wf_free(c->code.wf); wf_free(c->imp.wf);
     ctx_free(c->code); ctx_free(c->imp);
@@ -598,7 +674,8 @@ void lic360_codec_destroy(lic360_codec* c) {
 int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const float* w_dev, const float* bias_dev,
                            const float* slope_dev) {
     LIC360_CHECK_ARG(c && (stream_id == 0 || stream_id == 1) && layer >= 0 && layer < 12 && w_dev && bias_dev, "bad arguments");
-    LIC360_CUDA(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    LIC360_CUDA(guard.err);
     NetDesc& n = stream_id == 0 ? c->code : c->imp;
     LIC360_CHECK_ARG(!n.act[layer] || slope_dev, "this layer has a PReLU: slope_dev must not be NULL");
     const size_t npf = lic360_cconv_wp_floats(n.nsets, n.Cin[layer], n.Cout[layer], n.G);
@@ -623,7 +700,8 @@ int lic360_codec_set_layer(lic360_codec* c, int stream_id, int layer, const floa
 
 int lic360_codec_encode(lic360_codec* c, const float* code_dev, const float* mask_dev, const float* imp_dev) {
     LIC360_CHECK_ARG(c && code_dev && mask_dev && imp_dev, "bad arguments");
-    LIC360_CUDA(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    LIC360_CUDA(guard.err);
     int rc = check_params(c->code);
     if (rc == LIC360_OK) rc = check_params(c->imp);
     if (rc) return rc;
@@ -726,12 +804,17 @@ struct GoRelease {
 
 // wait for the rows of step p without synchronising the stream (a later kernel of the step graph may still be running)
 static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
-    volatile int* f = n.flag_host;
+    const int* f = n.flag_host;
     const auto t0 = clk::now();
     const int nf = n.nflags;
+    bool dev_abort = false;
+    // acquire loads: the rows the device wrote before raising a flag are read (non-atomically) by the coder right after
     auto ready = [&]() {
-        for (int i = 0; i < nf; i++)
-            if (f[i] != p + 1) return false;
+        for (int i = 0; i < nf; i++) {
+            const int v = __atomic_load_n(f + i, __ATOMIC_ACQUIRE);
+            if (v < 0) { dev_abort = true; return true; }
+            if (v != p + 1) return false;
+        }
         return true;
     };
     for (unsigned spins = 1; !ready(); spins++) {
@@ -750,6 +833,10 @@ static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
         __builtin_ia32_pause();
 #endif
         if ((spins & 0x7F) == 0) sched_yield();  // several ranks / images per box: do not starve the other polling threads
+    }
+    if (dev_abort) {
+        set_error("codec: step %d: a chain cluster gave up waiting for the other nets' clusters (too many decodes in flight on this device?)", p);
+        return LIC360_ERR_CUDA;
     }
     return LIC360_OK;
 }
@@ -869,7 +956,8 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
 int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, const uint8_t* code_bytes, long n_code,
                         float* code_out_dev, float* mask_out_dev) {
     LIC360_CHECK_ARG(c && imp_bytes && code_bytes && code_out_dev && mask_out_dev && n_imp >= 0 && n_code >= 0, "bad arguments");
-    LIC360_CUDA(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    LIC360_CUDA(guard.err);
     int rc = check_params(c->code);
     if (rc == LIC360_OK) rc = check_params(c->imp);
     if (rc) return rc;
@@ -913,10 +1001,11 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         c->t_imp = ms_since(t0);
     };
     if (c->mode == 0) {
-        std::thread worker(imp_loop);
+        ChainSlot slot(c->device, c->chain_cap);  // queues here when the device already runs as many decodes as it can hold
+        c->imp_worker.submit(imp_loop);
         rc = decode_stream(c, c->code, true);
         if (rc) c->abort_flag.store(1);
-        worker.join();
+        c->imp_worker.wait();
     } else {
         imp_loop();
         if (rc_imp == LIC360_OK) rc = decode_stream(c, c->code, true);

@@ -7,7 +7,7 @@
 // (ArithmeticCoder.cpp:56-68) are collapsed with count-leading-zeros into one multi-bit shift for the
 // "matching top bits" phase and one for the underflow phase, bits go through a 64-bit accumulator instead of an
 // iostream, and the power-of-two total (65536 for every table of this codec) turns the two divisions of the range
-// update into shifts.  tests/test_coder.py checks byte-identical streams against oracle/_ref/libref_coder.so
+// update into shifts.  tests/test_oracle_coder.py checks byte-identical streams against oracle/_ref/libref_coder.so
 // (the reference's own classes).
 #include <stdint.h>
 #include <stdio.h>
@@ -150,6 +150,7 @@ int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows) {
     for (int i = 0; i < nrows; i++) {
         const uint16_t* r = rows + (size_t)i * 8;
         if (!((r[7] >> 8) & 1)) continue;  // mask < 0.5: not coded (coder.cpp:79)
+        if (r[7] & 8) { set_error("coder: symbol out of range in packed row %d", i); return LIC360_ERR_CODER; }
         const int s = r[7] & 7;
         int rc = ac_update<false>(c, gmm_bin(r, s), gmm_bin(r, s + 1), 65536);
         if (rc) return rc;

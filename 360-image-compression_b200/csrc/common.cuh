@@ -54,6 +54,37 @@ inline int stream_grid(size_t work, int per_cta, int ctas_per_sm = 8) {
         }                                                                                     \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember the largest value raised so far for
+// every device, so that an op or codec created on cuda:1 after cuda:0 in the same process raises it there as well.
+constexpr int kMaxDevices = 64;
+struct SmemAttr {
+    size_t raised[kMaxDevices];
+    SmemAttr() { for (int i = 0; i < kMaxDevices; i++) raised[i] = 48 * 1024; }
+    template <typename F>
+    cudaError_t ensure(F func, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+        if (bytes <= raised[dev]) return cudaSuccess;
+        e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) raised[dev] = bytes;
+        return e;
+    }
+};
+
+// the codec entry points bind their device for the duration of the call and give the caller's current device back
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // wavefront slab of step psum (reference: cconv_dc_cuda.cu:113-117)
 inline void slab_of(const int32_t* plan, int H, int W, int G, int psum, int* start, int* len) {
     int la = psum >= G ? psum - G + 1 : 0;

@@ -560,11 +560,10 @@ int fill_conv_args(ConvArgs& a, const float* x, const float* wp, const float* wq
 }
 
 cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(cconv_ec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_SMEM_BYTES);
+    static SmemAttr ec_attr;  // per device (a process-wide flag left cuda:1 at the 48 KB default)
+    {
+        cudaError_t e = ec_attr.ensure(cconv_ec_kernel, EC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int ny = (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, nxy = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
     const int pair = (long long)nxy * ny * a.N > 2 * 148 ? 1 : 0;  // more than one wave of CTAs (2 per SM): balance them in pairs
@@ -589,12 +588,9 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
                 tap_cap = std::max(tap_cap, m);
             }
         const size_t rq_smem = ((size_t)2 * tap_cap * a.cin_g + (size_t)2 * nqb * 32) * sizeof(float4);
-        static size_t rq_attr = 48 * 1024;
-        if (rq_smem > rq_attr) {
-            e = cudaFuncSetAttribute(cconv_ec_rqb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rq_smem);
-            if (e != cudaSuccess) return e;
-            rq_attr = rq_smem;
-        }
+        static SmemAttr rq_attr;
+        e = rq_attr.ensure(cconv_ec_rqb_kernel, rq_smem);
+        if (e != cudaSuccess) return e;
         dim3 grid2((a.H * a.W + 31) / 32, a.nchunk, a.N), block2(32, 2 * nqb);
         cconv_ec_rqb_kernel<<<grid2, block2, rq_smem, s>>>(a, nqb, tap_cap);
     }
@@ -613,11 +609,10 @@ cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start
     const int nseg = nblk + 2 * nqb;
     if (nseg > 32) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)nseg * 32 * sizeof(float4) + DC_BAND * sizeof(int) + (size_t)nseg * DC_WARP_FLOATS * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(cconv_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemAttr dc_attr;
+    {
+        cudaError_t e = dc_attr.ensure(cconv_dc_kernel, smem);
         if (e != cudaSuccess) return e;
-        attr_smem = smem;
     }
     dim3 grid(ndiag * parts, a.cpg4, a.N), block(32, nseg);
     cconv_dc_kernel<<<grid, block, smem, s>>>(a, psum, nblk, nqb, parts, steps, ctr);

@@ -634,16 +634,36 @@ __device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d,
 // resident without needing anything from the waiting ones: no deadlock).  A separate, non-inlined function: its register
 // needs (erff, the 9-bin row) stay out of the chain's layer loop.
 __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& rows, int psum, int start, int len, int tid, int nt) {
+    __shared__ int s_abort;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         atomicAdd(rows.sync, 1);
         const int target = (psum + 1) * (int)gridDim.x;
-        while (*reinterpret_cast<volatile int*>(rows.sync) < target) {}
+        // Bail-out: with more decodes in flight than the device can keep resident (codec.cu bounds that with a per-device
+        // semaphore) a sibling cluster might never be placed; give up after ~2 s instead of spinning forever, the host sees the
+        // negative flag and fails the decode.
+        unsigned long long t0 = 0, t1 = 0;
+        int ab = 0;
+        for (unsigned spins = 1; *reinterpret_cast<volatile int*>(rows.sync) < target; spins++) {
+            if ((spins & 0x3FFF) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                else if (t1 - t0 > 2000000000ull) { ab = 1; break; }
+            }
+        }
+        s_abort = ab;
         __threadfence();
         WF_TRACE_MIN(net.G, psum, WF_TR_ROWS0);
     }
     __syncthreads();
+    if (s_abort) {
+        if (tid == 0) {
+            __threadfence_system();
+            reinterpret_cast<volatile int*>(rows.flag)[blockIdx.x] = -(psum + 1);
+        }
+        return;
+    }
     const int G = net.G, H = net.H, W = net.W, HW = H * W;
     const float* y = net.L[WF_LAYERS - 1].oc;
     // 4 lanes per symbol, lane j computes bins j + 1 and j + 5 (the 21 erff of a row are the latency of this phase; with 8 lanes
@@ -687,6 +707,7 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();  // thread 0's own fence between the barrier and the flag (as rows_done() in codec.cu)
         reinterpret_cast<volatile int*>(rows.flag)[blockIdx.x] = psum + 1;
         WF_TRACE_MAX(net.G, psum, WF_TR_ROWS1);
     }
@@ -1140,6 +1161,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain1_kernel(const __grid_constant
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();  // thread 0's own fence between the barrier and the flag
         *reinterpret_cast<volatile int*>(rows.flag) = sd.psum + 1;
         WF_TRACE_MAX(net.G, sd.psum, WF_TR_ROWS1);
     }
@@ -1232,23 +1254,13 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     e.prev_wcap = 0;
     for (int l = 0; l < WF_LAYERS; l++) e.prev_wcap = std::max(e.prev_wcap, TAPS * n.L[l].cin_g);
     e.prev_smem = ((size_t)e.prev_wcap + (size_t)e.nqb_max * 32) * sizeof(float4);
-    static size_t prev_attr = 48 * 1024;
-    if (e.prev_smem > prev_attr) {
-        LIC360_CUDA(cudaFuncSetAttribute(wf_prev_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.prev_smem));
-        LIC360_CUDA(cudaFuncSetAttribute(wf_prev_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.prev_smem));
-        prev_attr = e.prev_smem;
-    }
-    // the attribute is per kernel, not per engine: only ever raise it (two engines with different channel counts share it)
-    static size_t old_attr = 48 * 1024, chain_attr = 48 * 1024;
-    if (e.old_smem > old_attr) {
-        LIC360_CUDA(cudaFuncSetAttribute(wf_old_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old_smem));
-        old_attr = e.old_smem;
-    }
-    static size_t old2_attr = 48 * 1024;
-    if (e.old2_smem > old2_attr) {
-        LIC360_CUDA(cudaFuncSetAttribute(wf_old2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.old2_smem));
-        old2_attr = e.old2_smem;
-    }
+    // the attribute is per kernel AND per device, not per engine: only ever raise it (two engines with different channel counts
+    // share it), and remember it for every device separately (SmemAttr, common.cuh)
+    static SmemAttr prev_attr_a, prev_attr_b, old_attr, old2_attr, chain_attr_g, chain_attr_4, chain_attr_1;
+    LIC360_CUDA(prev_attr_a.ensure(wf_prev_kernel<320>, e.prev_smem));
+    LIC360_CUDA(prev_attr_b.ensure(wf_prev_kernel<1024>, e.prev_smem));
+    LIC360_CUDA(old_attr.ensure(wf_old_kernel, e.old_smem));
+    LIC360_CUDA(old2_attr.ensure(wf_old2_kernel, e.old2_smem));
     // chain kernels: one cluster per net.  16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
     // else the portable maximum of 8.
     LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1293,12 +1305,9 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         // The old-term kernel of the next step runs concurrently (programmatic dependent launch): claim the whole shared
         // memory of the SM so that none of its CTAs lands next to a chain CTA and steals its issue slots.
         if (!getenv("LIC360_WF_SHARE_SM")) e.chain_smem = std::max(e.chain_smem, (size_t)196 * 1024);
-        if (e.chain_smem > chain_attr) {
-            LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-            LIC360_CUDA(cudaFuncSetAttribute(wf_chain4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-            LIC360_CUDA(cudaFuncSetAttribute(wf_chain1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.chain_smem));
-            chain_attr = e.chain_smem;
-        }
+        LIC360_CUDA(chain_attr_g.ensure(wf_chain_kernel<384>, e.chain_smem));
+        LIC360_CUDA(chain_attr_4.ensure(wf_chain4_kernel, e.chain_smem));
+        LIC360_CUDA(chain_attr_1.ensure(wf_chain1_kernel, e.chain_smem));
         if (e.cluster <= 8) break;
         // can nsets clusters of this size be resident at once?
         cudaLaunchConfig_t cfg;
@@ -1316,6 +1325,23 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
         cudaGetLastError();
     }
     return LIC360_OK;
+}
+
+// How many decodes may run their code-stream chain concurrently on this device without risking the deadlock of partially
+// resident grids: the chain kernel's clusters wait for each other at a global counter (wf_chain4_rows), so ALL nsets clusters of
+// every running chain must be resident at once.
+int wf_chain_capacity(const WfEngine& e) {
+    if (!e.chain4) return 1 << 20;  // the other chain kernels have no inter-cluster wait
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(e.dev.nsets * e.cluster); cfg.blockDim = dim3(e.chain_threads); cfg.dynamicSmemBytes = e.chain_smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = e.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = e.cluster > 1 ? 1 : 0;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, wf_chain4_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return std::max(1, nclusters / e.dev.nsets);
 }
 
 const void* wf_old_kernel_ptr() { return reinterpret_cast<const void*>(&wf_old_kernel); }

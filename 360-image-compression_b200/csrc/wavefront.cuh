@@ -83,6 +83,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
             const int* ctr_dev, int nsteps, int max_len);
 void wf_set_layer(WfEngine& e, int l, const float* wp, const float* wq, const float* bias, const float* slope);
 void wf_free(WfEngine& e);
+int wf_chain_capacity(const WfEngine& e);  // decodes whose code-stream chains may be in flight together on the device
 const void* wf_old_kernel_ptr();
 const void* wf_old2_kernel_ptr();  // to give the old-term kernel node its own (lowest) priority in the step graph
 cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)

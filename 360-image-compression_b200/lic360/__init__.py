@@ -17,7 +17,7 @@ import torch
 from ._lib import LIB, check, cstream, ptr, ptr_or_null
 
 __all__ = [
-    "CconvDcOp", "CconvEcOp", "CodeContexOp", "Coder", "ContexShiftOp", "ContextReshapeOp", "DquantOp", "DtowOp",
+    "CconvDcOp", "CconvEcOp", "CodeContexOp", "Coder", "ContexShiftOp", "ContextReshapeOp", "DquantOp", "DtowOp", "ProjectsOp",
     "EntropyGmmOp", "EntropyGmmTableOp", "EntropyTableOp", "Imp2maskOp", "ImpMapOp", "MaskConstrainOp", "QuantOp",
     "ScaleOp", "SphereCutEdgeOp", "SphereLatScaleOp", "SpherePadOp", "SphereTrimOp", "TileAddOp", "TileExtractOp",
     "TileInputOp", "launch_count",
@@ -37,8 +37,35 @@ def _f32(t, name="tensor"):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _on_tensor_device(fn):
+    """Run an op method with the CUDA device of its first tensor argument current (and give the caller's device back):
+    the kernels are launched on `cstream(x)`, a stream of x's device, which is only legal while that device is current.
+    The reference binds the device once per op (base_opt.hpp:20-23); here several GPUs per process are a supported mode
+    (the module layer keeps {gid: op} dicts), so every call is guarded."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class _BaseOp(object):
     """base_opt (base_opt.hpp:4-80): device binding + cached output buffers."""
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        for name, fn in list(vars(cls).items()):
+            if callable(fn) and (name.startswith("forward") or name.startswith("backward")):
+                setattr(cls, name, _on_tensor_device(fn))
 
     def __init__(self, device=0, timeit=False):
         self.device_ = -1
@@ -731,6 +758,57 @@ class DtowOp(_BaseOp):
         bd = self._bottoms(top_diff, [(n, c, h, w)])
         check(LIB.lic360_dtow(ptr(top_diff), ptr(bd[0]), on, oc, oh, ow, self.stride_, int(not self.d2w_),
                               cstream(top_diff)))
+        return bd
+
+
+class ProjectsOp(_BaseOp):
+    """projects_opt (projects.hpp:6-34; main.cpp:6-10) -- SURVEY s8(f)-2: the 14 viewports of MultiProject.
+    theta / phi: 14 angles each in units of pi, fov in units of pi (projects.hpp:8-19)."""
+
+    def __init__(self, h_out, w_out, theta, phi, fov=0.33333, near=False, device=0, timeit=False):
+        self.h_out_, self.w_out_, self.fov_, self.near_ = int(h_out), int(w_out), float(fov), bool(near)
+        if len(theta) < 14 or len(phi) < 14:
+            raise RuntimeError("lic360: ProjectsOp needs 14 theta and 14 phi values")
+        self._theta = (ctypes.c_float * 14)(*[float(v) for v in theta[:14]])
+        self._phi = (ctypes.c_float * 14)(*[float(v) for v in phi[:14]])
+        self._xyz = self._tf = None
+        self._hw = None
+        _BaseOp.__init__(self, device, timeit)
+
+    def _on_init(self):  # projects_opt::init: the rays are rebuilt when the op moves to another device
+        self._xyz = self._tf = None
+        self._hw = None
+
+    def _geometry(self, x):
+        n, c, h, w = x.shape
+        inner = self.h_out_ * self.w_out_
+        if self._xyz is None or self._xyz.device != x.device:
+            self._xyz = torch.empty((14, inner, 3), dtype=torch.float32, device=x.device)
+            self._tf = torch.empty((14, inner, 2), dtype=torch.float32, device=x.device)
+            check(LIB.lic360_projects_init(ptr(self._xyz), self.h_out_, self.w_out_, self._theta, self._phi, self.fov_, cstream(x)))
+            self._hw = None
+        if self._hw != (h, w):  # projects_opt::reshape -> update()
+            check(LIB.lic360_projects_update(ptr(self._xyz), ptr(self._tf), self.h_out_, self.w_out_, h, w, cstream(x)))
+            self._hw = (h, w)
+
+    def forward(self, x):
+        x = _f32(x)
+        n, c, h, w = x.shape
+        self._geometry(x)
+        self._reshape((n, c, h, w))
+        top = self._tops(x, [(n * 14, c, self.h_out_, self.w_out_)])
+        check(LIB.lic360_projects_forward(ptr(x), ptr(self._tf), ptr(top[0]), n * c, h, w, self.h_out_, self.w_out_,
+                                          int(self.near_), cstream(x)))
+        return top
+
+    def backward(self, top_diff):
+        top_diff = _f32(top_diff)
+        if self._shape is None or self._tf is None:
+            raise RuntimeError("lic360: ProjectsOp.backward called before forward")
+        n, c, h, w = self._shape
+        bd = self._bottoms(top_diff, [(n, c, h, w), (n, c, h, w)])
+        check(LIB.lic360_projects_backward(ptr(top_diff), ptr(self._tf), ptr(bd[0]), ptr(bd[1]), n * c, h, w, self.h_out_,
+                                           self.w_out_, int(self.near_), cstream(top_diff)))
         return bd
 
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "lic360_sphere_cut_edge": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lic360_sphere_lat_scale": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "lic360_dtow": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "lic360_projects_init": (_I, [_P, _I, _I, _P, _P, _F, _P]),
+    "lic360_projects_update": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "lic360_projects_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "lic360_projects_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "lic360_coder_create": (_P, [ctypes.c_char_p, _F]),
     "lic360_coder_destroy": (None, [_P]),
     "lic360_coder_reset_fname": (_I, [_P, ctypes.c_char_p]),

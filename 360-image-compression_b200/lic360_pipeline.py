@@ -72,12 +72,38 @@ class FusedCodec(object):
         if not h:
             check(1)
         self._h = ctypes.c_void_p(h)
-        for sid, key in ((0, 'code'), (1, 'imp')):
+        # the codec packs the weights on its OWN stream: whatever produced them on torch's stream must have finished
+        torch.cuda.current_stream(self.dev).synchronize()
+        for sid, key, G, cpg, nlast, nsets in ((0, 'code', 48, 4, 3, 3), (1, 'imp', 1, 144, 49, None)):
             p = params[key]
             for layer, lk in enumerate(LAYER_KEYS):
+                cin = G * (1 if layer == 0 else cpg)
+                cout = G * (nlast if layer == 11 else cpg)
+                lead = () if nsets is None else (nsets,)
+                w = self._param(p[lk + '.weight'], lead + (cout, cin, 5, 5), lk + '.weight')
+                b = self._param(p[lk + '.bias'], lead + (cout,), lk + '.bias')
                 slope = p.get(lk + '.relu')
-                check(LIB.lic360_codec_set_layer(self._h, sid, layer, p[lk + '.weight'].data_ptr(), p[lk + '.bias'].data_ptr(),
+                if slope is not None:
+                    slope = self._param(slope, lead + (cout,), lk + '.relu')
+                elif layer != 11:
+                    raise RuntimeError("FusedCodec: %s.%s.relu is missing" % (key, lk))
+                check(LIB.lic360_codec_set_layer(self._h, sid, layer, w.data_ptr(), b.data_ptr(),
                                                  None if slope is None else slope.data_ptr()))
+
+    def _param(self, t, shape, name):
+        """float32, contiguous, on the codec's device, of the reference's shape -- anything else would be read as garbage
+        (or fault) by the native packer."""
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.dev:
+            raise RuntimeError("FusedCodec: parameter %s must live on %s" % (name, self.dev))
+        if t.dtype != torch.float32:
+            raise RuntimeError("FusedCodec: parameter %s must be float32 (got %s)" % (name, t.dtype))
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError("FusedCodec: parameter %s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+        t = t.detach()
+        if not t.is_contiguous():
+            t = t.contiguous()
+            torch.cuda.current_stream(self.dev).synchronize()  # the copy ran on torch's stream, the packer reads on the codec's
+        return t
 
     def __del__(self):
         h = getattr(self, '_h', None)

@@ -155,6 +155,23 @@ int lic360_sphere_lat_scale(const float* in_dev, const float* weight_dev, float*
 /* ---- DtowOp (main.cpp:36-40, dtow_cuda.cu:77-175) -- SURVEY s8(f)-1 "next" row --------------------------- */
 int lic360_dtow(const float* in_dev, float* out_dev, int N, int C, int H, int W, int stride, int d2w, void* stream);
 
+/* ---- ProjectsOp (main.cpp:6-10, projects.hpp:6-34, projects_cuda.cu) -- SURVEY s8(f)-2 "next" row: MultiProject --------------
+ * The 14 rectilinear viewports (h_out x w_out each) of an ERP image, bilinear or nearest; used by `--test` for viewport PSNR / SSIM
+ * (lic360_demo.py:424-441) and by the training loss (trainDDP_IMP_ENT.py:33-36).
+ *   init    : rays of all viewport pixels, xyz_dev (14, h_out*w_out, 3); theta14 / phi14 / fov in units of pi as the reference
+ *             constructor takes them (projects.hpp:8-19, projects_cuda.cu:84-126)
+ *   update  : ERP sampling coordinates for an H x W input, tf_dev (14, h_out*w_out, 2) = (x, y) (projects_cuda.cu:51-68,127-136);
+ *             call when the input size changes (projects_opt::reshape)
+ *   forward : in (NC = N*C planes, H, W) -> out (14*N, C, h_out, w_out), viewport-major: out[(v*NC + plane)*h_out*w_out + ps] (:181-252)
+ *   backward: top_diff (same layout as out) -> bottom_diff (NC, H, W) and the accumulated weights count (NC, H, W), both zeroed
+ *             first (:257-329; fp32 atomics, so the sums are order-dependent in their last bits like the reference's)        */
+int lic360_projects_init(float* xyz_dev, int h_out, int w_out, const float* theta14, const float* phi14, float fov, void* stream);
+int lic360_projects_update(const float* xyz_dev, float* tf_dev, int h_out, int w_out, int H, int W, void* stream);
+int lic360_projects_forward(const float* in_dev, const float* tf_dev, float* out_dev, int NC, int H, int W, int h_out, int w_out,
+                            int nearest, void* stream);
+int lic360_projects_backward(const float* top_diff_dev, const float* tf_dev, float* bottom_diff_dev, float* count_dev, int NC, int H,
+                             int W, int h_out, int w_out, int nearest, void* stream);
+
 /* ---- Coder (main.cpp:132-143, coder.h:10-63, coder.cpp:30-114; ArithmeticCoder.cpp, BitIoStream.cpp) -----
  * Same bitstream format (32-bit state range coder, MSB-first bits, `1` terminator + zero padding).
  * Tables are int32 rows of ncode+1 cumulative counts, total = row[ncode].                                   */

@@ -371,6 +371,39 @@ def dtow(x, stride, d2w):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ MultiProject
+_pj_c = _sig("orc_projects_coords", [_P, _I, _I, _P, _P, _F, _I, _I])
+_pj_f = _sig("orc_projects_forward", [_P, _P, _P, _I, _I, _I, _I, _I])
+_pj_b = _sig("orc_projects_backward", [_P, _P, _P, _P, _I, _I, _I, _I, _I])
+PROJECT_THETAS = [-0.5, 0, 0.5, 1, -0.5, 0, 0.5, 1, -0.5, 0, 0.5, 1, 0, 0]   # MultiProject.py:28-29
+PROJECT_PHIS = [0, 0, 0, 0, 0.25, 0.25, 0.25, 0.25, -0.25, -0.25, -0.25, -0.25, 0.5, -0.5]
+
+
+def projects_coords(h_out, w_out, fov, H, W, thetas=PROJECT_THETAS, phis=PROJECT_PHIS):
+    tf = np.zeros((14, h_out * w_out, 2), np.float32)
+    th, ph = np.asarray(thetas, np.float32), np.asarray(phis, np.float32)
+    _pj_c(_p(tf), h_out, w_out, _p(th), _p(ph), float(fov), H, W)
+    return tf
+
+
+def projects_forward(x, h_out, w_out, fov, near=False):
+    x = _f(x)
+    N, C, H, W = x.shape
+    tf = projects_coords(h_out, w_out, fov, H, W)
+    out = np.zeros((14 * N, C, h_out, w_out), np.float32)
+    _pj_f(_p(x), _p(tf), _p(out), N * C, H, W, h_out * w_out, int(near))
+    return out
+
+
+def projects_backward(top, shape, h_out, w_out, fov, near=False):
+    top = _f(top)
+    N, C, H, W = shape
+    tf = projects_coords(h_out, w_out, fov, H, W)
+    grad, count = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+    _pj_b(_p(top), _p(tf), _p(grad), _p(count), N * C, H, W, h_out * w_out, int(near))
+    return grad, count
+
+
 # ------------------------------------------------------------------------------------------------ coders
 for _n, _a, _r in (("orc_ac_new", [], _P), ("orc_ac_free", [_P], None), ("orc_ac_error", [_P], _I),
                    ("orc_ac_start_encoder", [_P], None), ("orc_ac_encode_rows", [_P, _P, _I, _P, _P, _I], None),

@@ -9,7 +9,8 @@ REF = os.environ.get("LIC360_REFERENCE_ROOT", "/root/reference")
 PKG = os.path.join(REF, "lic360_operator")
 WANT = ["CconvDc", "CconvDcBatch", "CconvEc", "CconvEcBatch", "CodeContex", "ContextReshape", "ContextShift", "Dquant", "Dtow",
         "EntropyBatchGmmTable", "EntropyGmm", "EntropyGmmTable", "EntropyTable", "Imp2mask", "ImpMap", "MaskConv2", "QUANT", "Scale",
-        "SphereCutEdge", "SphereLatScaleNet", "SpherePad", "SphereTrim", "TileAdd", "TileExtract", "TileExtractBatch", "TileInput"]
+        "SphereCutEdge", "SphereLatScaleNet", "SpherePad", "SphereTrim", "TileAdd", "TileExtract", "TileExtractBatch", "TileInput",
+        "MultiProject"]
 
 
 def sig(fn):

@@ -1,6 +1,8 @@
 """CPU: pins the oracle (oracle/lic360_oracle.c) with the independent formulations the reference itself contains
 (SURVEY.md s8c): masked conv2d == CconvEc == CconvDc-wavefront, the documented index-plan example, adjointness of
 forward/backward pairs, inverse pairs, and table invariants the arithmetic coder asserts."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -223,3 +225,61 @@ def test_config1_cpu_entropy_round_trip():
         pout = dec.decode_rows(tab.astype(np.int32), tables[p][1])
     O.tile_input(pout, frame, 1, G, H, W, -3.5, 1.0, 3, idx, plan, H + W + G - 2)
     assert np.array_equal(frame[0:1] + 3.5 * mask, q * mask)
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs golden
+GOLDEN_OPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_golden.npz")
+
+
+def _golden_cases():
+    from op_cases import CASES
+    if not os.path.exists(GOLDEN_OPS):
+        return []
+    files = set(np.load(GOLDEN_OPS).files)
+    return [c for c in CASES if any(f.startswith(c.name + "/") for f in files)]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=[c.name for c in _golden_cases()])
+def test_oracle_against_reference_golden(case):
+    """The oracle is pinned on the CPU, without a GPU: its output for every op case is compared with what the UNMODIFIED
+    reference CUDA extension produced for the same seeded inputs on a B200 (tests/golden/ops_golden.npz, make_golden.py).
+    Tiers as in tests/test_gpu_ops.py: exact keys bit for bit (SHA-256 for the large ones), expf/erff-derived integers within one
+    count on a tiny fraction (glibc vs libdevice), floats within the case's relative tolerance."""
+    import hashlib
+    from util import rel_err
+    gold = np.load(GOLDEN_OPS)
+    keys = [k[len(case.name) + 1:] for k in gold.files if k.startswith(case.name + "/")]
+    if case.levels_from_device:
+        pytest.skip("needs the device's exp() levels as an input")
+    exp = case.oracle()
+    checked = 0
+    for k in keys:
+        ref = gold[case.name + "/" + k]
+        if k.endswith("#sha256"):
+            base = k[:-7]
+            if base in case.exact and base in exp:
+                assert hashlib.sha256(np.ascontiguousarray(exp[base]).tobytes()).hexdigest() == str(ref), (case.name, base)
+                checked += 1
+            continue
+        if k.endswith("#sub"):
+            base = k[:-4]
+            if base not in exp:
+                continue
+            sub = np.ascontiguousarray(exp[base]).reshape(-1)[::exp[base].size // 8192][:8192]
+            assert rel_err(sub, ref) <= case.oracle_close.get(base, case.close[base]), (case.name, base, rel_err(sub, ref))
+            checked += 1
+            continue
+        if k not in exp or k in case.skip_ref:
+            continue
+        a = exp[k]
+        assert a.shape == ref.shape, (case.name, k, a.shape, ref.shape)
+        if k in case.exact:
+            assert np.array_equal(a, ref), "%s/%s: %d of %d entries differ" % (case.name, k, int((a != ref).sum()), a.size)
+        elif k in case.libm:
+            d = np.abs(a.astype(np.int64) - ref.astype(np.int64))
+            assert d.max() <= 1 and (d > 0).mean() <= 5e-3, "%s/%s: max diff %d, frac %.4f" % (case.name, k, d.max(), (d > 0).mean())
+        else:
+            tol = case.oracle_close.get(k, case.close[k])
+            assert rel_err(a, ref) <= tol, "%s/%s: rel err %.3g > %.1g" % (case.name, k, rel_err(a, ref), tol)
+        checked += 1
+    assert checked > 0
