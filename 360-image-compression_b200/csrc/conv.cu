@@ -337,6 +337,80 @@ __global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq_kernel(const ConvAr
     rq_epilogue(a, n, set, chunk, g_out, pos, RQ[0], RQ[1]);
 }
 
+// R / Q pass of the many-group nets (cin_g == 4, one 4-channel output chunk per group: every hidden and the last layer of the code
+// stream).  The generic kernel above fetches its 200 activations per output straight from L2 (coalesced, but 40 channel planes
+// per output group and no reuse between the 25 taps: ~5 TB/s of L1/L2 traffic, 180 us per layer at 512x1024).  Here a CTA owns an
+// 8x32 spatial tile and TWO adjacent output groups g, g+1: the 11 input groups g-5 .. g+5 their taps select (44 channels) are
+// staged once in shared memory with their 2-pixel halo (zero-filled outside the image / outside [0, G): the skipped terms of the
+// canonical order become exact +0 products), and all 400 taps of a position are shared-memory reads.  Per-output arithmetic and
+// order are those of cconv_ec_rq_kernel<4> (canonical order, header of this file).
+constexpr int RQT_GROUPS = 11;                        // input groups staged per CTA
+constexpr int RQT_CH = RQT_GROUPS * 4;
+constexpr int RQT_SMEM_BYTES = (RQT_CH * XH * XW + 2 * 2 * TAPS * 4 * 4) * (int)sizeof(float);  // x tiles + [pair][cls][tap][c] float4
+
+__global__ void __launch_bounds__(256, 2) cconv_ec_rq_tile_kernel(const ConvArgs a) {
+    extern __shared__ float4 rqt_smem[];
+    float4* wsm = rqt_smem;                                        // [2 groups][2 classes][TAPS][4] float4
+    float* xs = reinterpret_cast<float*>(rqt_smem + 2 * 2 * TAPS * 4);  // [RQT_CH][XH][XW]
+    const int tid = threadIdx.x;
+    const int tiles_w = (a.W + TW - 1) / TW;
+    const int w0 = (blockIdx.x % tiles_w) * TW, h0 = (blockIdx.x / tiles_w) * TH;
+    const int g0 = 2 * blockIdx.y, n = blockIdx.z, set = n / a.per;
+    const int H = a.H, W = a.W, HW = a.H * a.W, G = a.G;
+    const int ncls = a.has_q ? 2 : 1;
+    // weights: wq [cls][set][chunk][tap][c] float4, chunk == group here
+    const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * (TAPS * 4);
+    const float4* wq4 = reinterpret_cast<const float4*>(a.wq);
+    for (int e = tid; e < 2 * 2 * TAPS * 4; e += 256) {
+        const int pr = e / (2 * TAPS * 4), cls = (e / (TAPS * 4)) % 2, r = e % (TAPS * 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g0 + pr < G && cls < ncls) v = __ldg(wq4 + cls * wq_cls + ((size_t)set * a.nchunk + g0 + pr) * (TAPS * 4) + r);
+        wsm[e] = v;
+    }
+    // activations: groups g0-5 .. g0+5, channel-planar tiles with halo
+    const unsigned xs_s = (unsigned)__cvta_generic_to_shared(xs);
+    const float* xn = a.x + (size_t)n * a.Cin * HW;
+    for (int e = tid; e < RQT_CH * XH * XW; e += 256) {
+        const int ch = e / (XH * XW), r = (e % (XH * XW)) / XW, c = e % XW;
+        const int grp = g0 - 5 + ch / 4;
+        const int h = h0 + r - 2, w = w0 + c - 2;
+        const bool ok = grp >= 0 && grp < G && h >= 0 && h < H && w >= 0 && w < W;
+        cp_async4(xs_s + 4u * e, ok ? xn + ((size_t)(grp * 4 + ch % 4) * H + h) * W + w : xn, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const int h = h0 + ty, w = w0 + tx;
+    if (h >= H || w >= W) return;
+    const int pos = h * W + w;
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+        const int g_out = g0 + pr;
+        if (g_out >= G) break;
+        float RQ[2][4];
+#pragma unroll
+        for (int cls = 0; cls < 2; cls++) {
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cls < ncls) {
+                const float4* ws = wsm + (pr * 2 + cls) * (TAPS * 4);
+#pragma unroll
+                for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+                    for (int kw = 0; kw < 5; kw++) {
+                        // input group g_out + 3 + cls - kh - kw = staged group index (that - (g0 - 5)) = 8 + pr + cls - kh - kw in [0, 10]
+                        const int sg = 8 + pr + cls - kh - kw;
+                        const float* xp = xs + (sg * 4) * (XH * XW) + (ty + kh) * XW + tx + kw;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) fma4(u, xp[c * (XH * XW)], ws[(kh * 5 + kw) * 4 + c]);
+                    }
+                }
+            }
+            RQ[cls][0] = 0.f + u.x; RQ[cls][1] = 0.f + u.y; RQ[cls][2] = 0.f + u.z; RQ[cls][3] = 0.f + u.w;
+        }
+        rq_epilogue(a, n, set, g_out, g_out, pos, RQ[0], RQ[1]);
+    }
+}
+
 __global__ void __launch_bounds__(640, 2) cconv_ec_rqb_kernel(const ConvArgs a, int nqb, int tap_cap) {
     extern __shared__ float4 rq_wsm[];  // [2 classes][tap_cap][cin_g] weights of the taps that select a valid group, then partials
     __shared__ int s_tap[2][TAPS], s_ntap[2];
@@ -573,7 +647,14 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int nqb = (a.cin_g + CB - 1) / CB;
-    if (nqb == 1) {
+    static const bool rq_tile_off = getenv("LIC360_EC_RQ_GENERIC") != nullptr;
+    if (a.cin_g == 4 && a.cpg4 == 1 && a.G >= 8 && !rq_tile_off) {
+        static SmemAttr rqt_attr;
+        e = rqt_attr.ensure(cconv_ec_rq_tile_kernel, RQT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        dim3 grid2(nxy, (a.G + 1) / 2, a.N);
+        cconv_ec_rq_tile_kernel<<<grid2, 256, RQT_SMEM_BYTES, s>>>(a);
+    } else if (nqb == 1) {
         const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);  // <= 12.8 KB
         dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);
         if (a.cin_g == 4) cconv_ec_rq_kernel<4><<<grid2, RQ_THREADS, rq_smem, s>>>(a);

@@ -209,6 +209,63 @@ __global__ void __launch_bounds__(256) quant_fwd_kernel(const float* __restrict_
     }
 }
 
+// The configured quantiser (8 levels, test/model_zoo.py:342) on vectorisable planes: one WARP per 1024-element piece of an (n,c) plane,
+// no CTA barriers; the channel's 8 levels sit in registers, every lane keeps a private histogram in two 64-bit words (4 x 16-bit
+// counters each: a lane sees at most 32 elements of a piece, a warp 1024), one shuffle reduction and at most 8 global atomics per
+// piece.  Same arithmetic per element as quant_fwd_kernel (quant_cuda.cu:46-76).
+constexpr int Q8_PIECE = 1024;
+__global__ void __launch_bounds__(256) quant_fwd8_kernel(const float* __restrict__ x, const float* __restrict__ lv, float* __restrict__ y,
+                                                         float* __restrict__ q, int32_t* __restrict__ qi, float* __restrict__ count,
+                                                         int NC, int C, int HW, int pieces_per_plane) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); job < NC * pieces_per_plane; job += warps_total) {
+        const int plane = job / pieces_per_plane, piece = job % pieces_per_plane;
+        const int c = plane % C;
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = __ldg(lv + c * 8 + j);
+        const int e0 = piece * Q8_PIECE, e1 = min(HW, e0 + Q8_PIECE);
+        const size_t base = (size_t)plane * HW;
+        unsigned long long h0 = 0, h1 = 0;
+        for (int e = e0 + lane * 4; e < e1; e += 128) {
+            const float4 t = *reinterpret_cast<const float4*>(x + base + e);
+            const float xv[4] = {t.x, t.y, t.z, t.w};
+            float yv[4], qv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float tmp = xv[k] - s[0];
+                int j;
+                if (tmp < 0) { j = 0; yv[k] = s[0]; }
+                else {
+                    j = 1;
+#pragma unroll
+                    for (int jj = 1; jj < 8; jj++) {   // first j with a negative remainder; lanes that found it stop subtracting
+                        if (j == jj) { tmp -= s[jj]; if (!(tmp < 0)) j = jj + 1; }
+                    }
+                    if (j == 8) j--;
+                    float sj = s[1];
+#pragma unroll
+                    for (int jj = 2; jj < 8; jj++) sj = j == jj ? s[jj] : sj;
+                    if (tmp + tmp + sj < 0) { tmp = tmp + sj; j--; }
+                    yv[k] = xv[k] - tmp;
+                }
+                qv[k] = (float)j;
+                if (j < 4) h0 += 1ull << (16 * j); else h1 += 1ull << (16 * (j - 4));
+            }
+            *reinterpret_cast<float4*>(y + base + e) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            if (q) *reinterpret_cast<float4*>(q + base + e) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+            *reinterpret_cast<int4*>(qi + base + e) = make_int4((int)qv[0], (int)qv[1], (int)qv[2], (int)qv[3]);
+        }
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) { h0 += __shfl_xor_sync(0xffffffffu, h0, k); h1 += __shfl_xor_sync(0xffffffffu, h1, k); }
+        if (lane < 8) {
+            const unsigned n = (unsigned)(((lane < 4 ? h0 : h1) >> (16 * (lane & 3))) & 0xFFFFull);
+            if (n) atomicAdd(count + c * 8 + lane, -(float)n);
+        }
+    }
+}
+
 // quant_cuda.cu:88-117 (dead-level repair + histogram decay), one thread per channel / element
 __global__ void quant_check_weight_kernel(float* __restrict__ weight, const float* __restrict__ count, int C, int levels) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
@@ -595,7 +652,10 @@ extern "C" int lic360_quant_forward(const float* x_dev, const float* wb_dev, flo
     const int chunk_elems = 256 * 4 * 4;  // 4 float4 per thread per chunk
     const int cpp = (HW + chunk_elems - 1) / chunk_elems;
     const int grid = stream_grid((size_t)N * C * cpp, 1);
-    if (v4) quant_fwd_kernel<4><<<grid, 256, 0, S_(stream)>>>(x_dev, levels_dev, y_dev, q_dev, qint_dev, count_dev, N * C, C, HW, L, cpp, chunk_elems);
+    if (v4 && L == 8) {
+        const int ppp = (HW + Q8_PIECE - 1) / Q8_PIECE;
+        quant_fwd8_kernel<<<stream_grid((size_t)N * C * ppp, 8), 256, 0, S_(stream)>>>(x_dev, levels_dev, y_dev, q_dev, qint_dev, count_dev, N * C, C, HW, ppp);
+    } else if (v4) quant_fwd_kernel<4><<<grid, 256, 0, S_(stream)>>>(x_dev, levels_dev, y_dev, q_dev, qint_dev, count_dev, N * C, C, HW, L, cpp, chunk_elems);
     else quant_fwd_kernel<1><<<grid, 256, 0, S_(stream)>>>(x_dev, levels_dev, y_dev, q_dev, qint_dev, count_dev, N * C, C, HW, L, cpp, chunk_elems);
     LAUNCH_CHECK();
     return LIC360_OK;

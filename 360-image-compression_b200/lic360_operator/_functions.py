@@ -37,11 +37,12 @@ class FwdBwd(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, op, inplace, x):
+        # In-place ops (SpherePad(inplace), SphereTrim) hand back x itself.  Like the reference's *_AF classes they do NOT tell
+        # autograd (no mark_dirty): the reference's models pad / trim tensors in place that a conv has already saved for its
+        # backward (train/model_zoo.py:15-30 and the like), which a version bump would turn into "modified by an inplace
+        # operation" errors -- the train/ scripts have to run unchanged, so the module layer keeps the reference's semantics.
         ctx.op = op
-        out = _op_of(op, x).forward(x)[0]
-        if inplace:
-            ctx.mark_dirty(x)
-        return out
+        return _op_of(op, x).forward(x)[0]
 
     @staticmethod
     def backward(ctx, grad):

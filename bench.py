@@ -273,39 +273,70 @@ def main():
     run(1, True)
     ms_e2e, _, _, _, _ = timed(args.steps, True)
 
-    # ---- secondary figure: the same work with several images in flight per GPU (one host thread + one codec each), so
-    # the host arithmetic coder of one image overlaps the GPU steps of the other
-    piped_ms = None
-    try:
-        if world > 1:
-            raise RuntimeError("single-GPU figure only (the host cores of the box are shared by all ranks)")
-        nfly = max(2, int(os.environ.get("LIC360_BENCH_IN_FLIGHT", "4" if world == 1 else "2")))  # each image has 2 polling host threads
-        codecs = [codec] + [pl.FusedCodec(params, H=H, W=W, gid=local_rank) for _ in range(nfly - 1)]
-        for cd in codecs:
-            cd.decode(*cd.encode(tq, tm, tl))
+    # ---- secondary figures: several images in flight per GPU (one codec + its host threads each), so that the host arithmetic coder
+    # of one image overlaps the GPU steps of another.  A queue of images is drained by `nfly` workers per rank.
+    def in_flight(codecs, images, repeat):
+        """images: list of (code, mask, levels) device tensors; every worker pulls the next image index until repeat * len(images)
+        images are coded; returns (ms of the slowest rank, all round trips exact)"""
+        import itertools
+        counter, lock = itertools.count(), threading.Lock()
+        total, res = repeat * len(images), [True] * len(codecs)
 
-        def worker(cd, n_img, res, k):
-            okk = True
-            for _ in range(n_img):
-                bi, bc = cd.encode(tq, tm, tl)
-                code, mup = cd.decode(bi, bc)
-            torch.cuda.synchronize()
-            res[k] = bool(torch.equal(code, tq * tm)) and okk
+        def worker(k, cd):
+            while True:
+                with lock:
+                    i = next(counter)
+                if i >= total:
+                    break
+                a, b, c = images[i % len(images)]
+                code, mup = cd.decode(*cd.encode(a, b, c))
+                res[k] = res[k] and bool(torch.equal(code, a * b)) and bool(torch.equal(mup, b))
 
         barrier()
-        res = [None] * nfly
         t0 = time.time()
-        th = [threading.Thread(target=worker, args=(cd, args.steps, res, k)) for k, cd in enumerate(codecs)]
+        th = [threading.Thread(target=worker, args=(k, cd)) for k, cd in enumerate(codecs)]
         for t_ in th:
             t_.start()
         for t_ in th:
             t_.join()
         torch.cuda.synchronize()
-        piped_ms = sh.max_over_ranks((time.time() - t0) * 1e3, dev)
-        piped_ok = all(res)
+        return sh.max_over_ranks((time.time() - t0) * 1e3, dev), all(res)
+
+    piped_ms = None
+    try:
+        # each image in flight has 2 polling host threads (importance + code stream): 4 per GPU alone on the box, 2 when N ranks share it
+        nfly = max(2, int(os.environ.get("LIC360_BENCH_IN_FLIGHT", "4" if world == 1 else "2")))
+        codecs = [codec] + [pl.FusedCodec(params, H=H, W=W, gid=local_rank) for _ in range(nfly - 1)]
+        for cd in codecs:
+            cd.decode(*cd.encode(tq, tm, tl))
+        piped_ms, piped_ok = in_flight(codecs, [(tq, tm, tl)], nfly * args.steps)
         del codecs
     except Exception as e:  # secondary figure only
         piped_ms, piped_ok = None, repr(e)
+
+    # ---- configs[2]: LIC3602K shape, 16 images of 1024x2048 (latent 128x256) sharded by image over the ranks (16 / N per GPU), queue
+    # drained by up to 4 (N = 1) or 2 (N > 1) codecs per GPU; no collective on the codec path
+    cfg3 = None
+    try:
+        if os.environ.get("LIC360_BENCH_NO_CONFIG3"):
+            raise RuntimeError("disabled by LIC360_BENCH_NO_CONFIG3")
+        n_img = max(1, 16 // world)
+        nfly3 = min(n_img, 4 if world == 1 else 2)
+        imgs3 = []
+        for i in range(n_img):
+            a, b, c = synthetic_latent(3000 + 16 * rank + i, 128, 256)
+            imgs3.append(tuple(torch.from_numpy(v).to(dev) for v in (a, b, c)))
+        codecs3 = [pl.FusedCodec(params, H=128, W=256, gid=local_rank) for _ in range(nfly3)]
+        for cd in codecs3:
+            cd.decode(*cd.encode(*imgs3[0]))
+        ms3, ok3 = in_flight(codecs3, imgs3, 1)
+        cfg3 = {"value": world * n_img * (1024 * 2048 / 1e6) / (ms3 / 1e3), "unit": "Mpx/s", "images": world * n_img, "images_per_gpu": n_img,
+                "in_flight_per_gpu": nfly3, "image": [1024, 2048], "latent": [1, 48, 128, 256], "ms_total": ms3, "round_trip_exact": ok3,
+                "timing": "host wall clock around all worker threads, max over ranks",
+                "note": "configs[2]: batch of 16 LIC3602K-shape images sharded by image, encode + decode of both streams of every image"}
+        del codecs3, imgs3
+    except Exception as e:  # secondary figure only
+        cfg3 = {"unavailable": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -387,6 +418,7 @@ def main():
         line["images_in_flight"] = {"value": world * nfly * args.steps * MPX / (piped_ms / 1e3), "unit": "Mpx/s", "images_in_flight_per_gpu": nfly,
                                         "round_trip_exact": piped_ok, "timing": "host wall clock around all worker threads, max over ranks",
                                         "note": "secondary figure; `value` and `e2e` are one image at a time"}
+    line["config3_1024x2048_batch16"] = cfg3
     if sampler:
         line["clocks"] = sampler.summary()
     if world == 1 and not args.no_cpu_baseline:

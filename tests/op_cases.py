@@ -482,6 +482,52 @@ _mk_quant("c5_ntop1", 2, 5, 3, 7, 8, 1, 602)
 _mk_quant("c192", 1, 192, 32, 64, 8, 2, 603)
 
 
+def _mk_quant_update(name, C, L, seed):
+    """QuantOp's periodic dead-level repair + histogram decay (quant_cuda.cu:88-134), reached through forward(..., train=True) on
+    every check_iters-th training call: the op rewrites the caller's weight and ncount tensors in place."""
+    def data():
+        r = rng(seed)
+        wb = (np.log(1. / (L + 1)) + 0.2 * r.standard_normal((C, L))).astype(np.float32)
+        wb[:, 0] = 0.1
+        cnt = (r.random((C, L)) * 50).astype(np.float32)
+        cnt[0, L - 3:] = 0          # dead top levels
+        cnt[1, 0] = 0               # dead first level
+        cnt[2, :] = 0               # everything dead
+        cnt[3, 2:] = 5e-4           # below the 1e-3 threshold
+        x = r.random((1, C, 4, 8)).astype(np.float32)
+        return wb, cnt, x
+
+    def run(b, dev):
+        wb, cnt, x = data()
+        twb, tcnt, tx = t(wb, dev), t(cnt, dev), t(x, dev)
+        op = b.QuantOp(C, L, 0.9, 2, 1, 0.1, 0, False)   # check_iters = 2: the third training call repairs
+        for _ in range(2):
+            op.forward(tx, twb, tcnt, True)
+        before = n(twb).copy()
+        op.forward(tx, twb, tcnt, True)
+        return {"weight_unchanged_before_check": before, "weight": n(twb).copy(), "ncount": n(tcnt).copy()}
+
+    def orc():
+        wb, cnt, _ = data()
+        w = wb.copy()
+        for i in range(C):
+            j = L - 1
+            while j > 1 and not cnt[i, j] >= 1e-3:
+                j -= 1
+            tmp = np.float32(w[i, j] - np.log(np.float32(L - j)))
+            w[i, j:] = tmp
+            if cnt[i, 0] < 1e-3:
+                w[i, 0] = np.float32(w[i, 0] + np.exp(w[i, 1]))
+                tmp = np.float32(np.log((np.exp(w[i, 1]) + np.exp(w[i, 2])) / np.float32(2)))
+                w[i, 1] = tmp
+                w[i, 2] = tmp
+        return {"weight_unchanged_before_check": wb, "weight": w, "ncount": (cnt * np.float32(0.9)).astype(np.float32)}
+    Case("quant_update_weight_" + name, run, orc, exact=("weight_unchanged_before_check",), close={"weight": 1e-6, "ncount": 1e-6})
+
+
+_mk_quant_update("c6", 6, 8, 621)
+
+
 def _mk_dquant(name, N, C, H, W, L, seed):
     def data():
         r = rng(seed)
