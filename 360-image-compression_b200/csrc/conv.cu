@@ -338,76 +338,104 @@ __global__ void __launch_bounds__(RQ_THREADS, 2) cconv_ec_rq_kernel(const ConvAr
 }
 
 // R / Q pass of the many-group nets (cin_g == 4, one 4-channel output chunk per group: every hidden and the last layer of the code
-// stream).  The generic kernel above fetches its 200 activations per output straight from L2 (coalesced, but 40 channel planes
-// per output group and no reuse between the 25 taps: ~5 TB/s of L1/L2 traffic, 180 us per layer at 512x1024).  Here a CTA owns an
-// 8x32 spatial tile and TWO adjacent output groups g, g+1: the 11 input groups g-5 .. g+5 their taps select (44 channels) are
-// staged once in shared memory with their 2-pixel halo (zero-filled outside the image / outside [0, G): the skipped terms of the
-// canonical order become exact +0 products), and all 400 taps of a position are shared-memory reads.  Per-output arithmetic and
-// order are those of cconv_ec_rq_kernel<4> (canonical order, header of this file).
-constexpr int RQT_GROUPS = 11;                        // input groups staged per CTA
-constexpr int RQT_CH = RQT_GROUPS * 4;
-constexpr int RQT_SMEM_BYTES = (RQT_CH * XH * XW + 2 * 2 * TAPS * 4 * 4) * (int)sizeof(float);  // x tiles + [pair][cls][tap][c] float4
+// stream).  The generic kernel above fetches its 200 activations per output straight from L2 (40 channel planes per output group,
+// no reuse between the 25 taps, one broadcast weight load per FMA4: ~5 TB/s of L1/L2 traffic, 180 us per layer at 512x1024).
+// Here a CTA owns an 8x32 spatial tile and FOUR adjacent output groups: the 13 input groups g0-5 .. g0+7 their taps select (52
+// channels) are staged once in shared memory with their halo, as aligned 16-byte cp.async chunks (rows start at column w0-4;
+// zero-filled outside the image / outside [0, G): the skipped terms of the canonical order become exact +0 products).  A warp owns a
+// PAIR of output groups on a 4-row x 16-column piece of the tile, a lane 2 positions (columns 8 apart): the previous-wavefront tap
+// of group g+1 and the same-wavefront tap of group g read the same activation, so 3 activation loads feed the 4 (group, class)
+// accumulators of a position and each broadcast weight vector feeds 2 positions.  112 KB per CTA: two CTAs per SM, one loads while
+// the other computes.  Per-output arithmetic and order are those of cconv_ec_rq_kernel<4> (canonical order, header of this file).
+constexpr int RQ4_G = 4;                          // output groups per CTA
+constexpr int RQ4_IN = RQ4_G + 9;                 // input groups staged: g0-5 .. g0+7
+constexpr int RQ4_XW = 40;                        // staged row: columns w0-4 .. w0+35 (ten float4); lane (ty, tx) -> bank 8*ty + tx
+constexpr int RQ4_PLANE = XH * RQ4_XW;
+constexpr int RQ4_W_F4 = RQ4_G * 2 * TAPS * 4;    // [group][class][tap][c] float4
+constexpr int RQ4_SMEM_BYTES = RQ4_W_F4 * 16 + RQ4_IN * 4 * RQ4_PLANE * 4;
 
 __global__ void __launch_bounds__(256, 2) cconv_ec_rq_tile_kernel(const ConvArgs a) {
     extern __shared__ float4 rqt_smem[];
-    float4* wsm = rqt_smem;                                        // [2 groups][2 classes][TAPS][4] float4
-    float* xs = reinterpret_cast<float*>(rqt_smem + 2 * 2 * TAPS * 4);  // [RQT_CH][XH][XW]
-    const int tid = threadIdx.x;
+    float4* wsm = rqt_smem;
+    float* xs = reinterpret_cast<float*>(rqt_smem + RQ4_W_F4);  // [RQ4_IN * 4][XH][RQ4_XW]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_w = (a.W + TW - 1) / TW;
     const int w0 = (blockIdx.x % tiles_w) * TW, h0 = (blockIdx.x / tiles_w) * TH;
-    const int g0 = 2 * blockIdx.y, n = blockIdx.z, set = n / a.per;
+    const int g0 = RQ4_G * blockIdx.y, n = blockIdx.z, set = n / a.per;
     const int H = a.H, W = a.W, HW = a.H * a.W, G = a.G;
     const int ncls = a.has_q ? 2 : 1;
     // weights: wq [cls][set][chunk][tap][c] float4, chunk == group here
     const size_t wq_cls = (size_t)(a.N / a.per) * a.nchunk * (TAPS * 4);
     const float4* wq4 = reinterpret_cast<const float4*>(a.wq);
-    for (int e = tid; e < 2 * 2 * TAPS * 4; e += 256) {
-        const int pr = e / (2 * TAPS * 4), cls = (e / (TAPS * 4)) % 2, r = e % (TAPS * 4);
+    for (int e = tid; e < RQ4_W_F4; e += 256) {
+        const int grp = e / (2 * TAPS * 4), cls = (e / (TAPS * 4)) % 2, r = e % (TAPS * 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g0 + pr < G && cls < ncls) v = __ldg(wq4 + cls * wq_cls + ((size_t)set * a.nchunk + g0 + pr) * (TAPS * 4) + r);
+        if (g0 + grp < G && cls < ncls) v = __ldg(wq4 + cls * wq_cls + ((size_t)set * a.nchunk + g0 + grp) * (TAPS * 4) + r);
         wsm[e] = v;
     }
-    // activations: groups g0-5 .. g0+5, channel-planar tiles with halo
+    // activations: warp w stages channels w, w+8, ...; 12 rows x 10 aligned float4 per channel (W % 4 == 0 is checked by the launcher)
     const unsigned xs_s = (unsigned)__cvta_generic_to_shared(xs);
     const float* xn = a.x + (size_t)n * a.Cin * HW;
-    for (int e = tid; e < RQT_CH * XH * XW; e += 256) {
-        const int ch = e / (XH * XW), r = (e % (XH * XW)) / XW, c = e % XW;
-        const int grp = g0 - 5 + ch / 4;
-        const int h = h0 + r - 2, w = w0 + c - 2;
-        const bool ok = grp >= 0 && grp < G && h >= 0 && h < H && w >= 0 && w < W;
-        cp_async4(xs_s + 4u * e, ok ? xn + ((size_t)(grp * 4 + ch % 4) * H + h) * W + w : xn, ok);
+    for (int ch = warp; ch < RQ4_IN * 4; ch += 8) {
+        const int grp = g0 - 5 + (ch >> 2);
+        const bool gok = grp >= 0 && grp < G;
+        const float* plane = xn + (size_t)(gok ? grp * 4 + (ch & 3) : 0) * HW;
+        for (int id = lane; id < XH * (RQ4_XW / 4); id += 32) {
+            const int r = id / (RQ4_XW / 4), c4 = id % (RQ4_XW / 4);
+            const int h = h0 + r - 2, w = w0 - 4 + 4 * c4;
+            const bool ok = gok && h >= 0 && h < H && w >= 0 && w + 3 < W;
+            cp_async16z(xs_s + 4u * (ch * RQ4_PLANE + r * RQ4_XW + 4 * c4), ok ? plane + (size_t)h * W + w : xn, ok);
+        }
     }
     cp_async_wait_all();
     __syncthreads();
-    const int tx = tid & 31, ty = tid >> 5;
-    const int h = h0 + ty, w = w0 + tx;
-    if (h >= H || w >= W) return;
-    const int pos = h * W + w;
+    // warp -> (pair of output groups, 4-row half, 16-column half); lane -> row ty, columns tx and tx + 8 of that piece
+    const int pi = warp >> 2, row = ((warp >> 1) & 1) * 4 + (lane >> 3), col = (warp & 1) * 16 + (lane & 7);
+    if (g0 + 2 * pi >= G) return;  // warp-uniform
+    float4 acc[2][4];  // [position j][pr * 2 + cls]
 #pragma unroll
-    for (int pr = 0; pr < 2; pr++) {
-        const int g_out = g0 + pr;
-        if (g_out >= G) break;
-        float RQ[2][4];
+    for (int j = 0; j < 2; j++)
 #pragma unroll
-        for (int cls = 0; cls < 2; cls++) {
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cls < ncls) {
-                const float4* ws = wsm + (pr * 2 + cls) * (TAPS * 4);
+        for (int k = 0; k < 4; k++) acc[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* wpair = wsm + (2 * pi) * 2 * TAPS * 4;
+#pragma unroll 1
+    for (int kh = 0; kh < 5; kh++) {
 #pragma unroll
-                for (int kh = 0; kh < 5; kh++) {
+        for (int kw = 0; kw < 5; kw++) {
+            // (pr, cls) reads input group g0 + 2pi + pr + cls + 3 - kh - kw = staged group 2pi + 8 + (pr + cls) - kh - kw;
+            // image column w0 + col + kw - 2 = staged column col + kw + 2
+            const float* xt = xs + ((2 * pi + 8 - kh - kw) * 4) * RQ4_PLANE + (row + kh) * RQ4_XW + col + kw + 2;
 #pragma unroll
-                    for (int kw = 0; kw < 5; kw++) {
-                        // input group g_out + 3 + cls - kh - kw = staged group index (that - (g0 - 5)) = 8 + pr + cls - kh - kw in [0, 10]
-                        const int sg = 8 + pr + cls - kh - kw;
-                        const float* xp = xs + (sg * 4) * (XH * XW) + (ty + kh) * XW + tx + kw;
+            for (int c = 0; c < 4; c++) {
+                float xv[3][2];
 #pragma unroll
-                        for (int c = 0; c < 4; c++) fma4(u, xp[c * (XH * XW)], ws[(kh * 5 + kw) * 4 + c]);
-                    }
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) xv[k][j] = xt[(k * 4 + c) * RQ4_PLANE + 8 * j];
+#pragma unroll
+                for (int pc = 0; pc < 4; pc++) {  // pc = pr * 2 + cls
+                    const float4 w4 = wpair[pc * (TAPS * 4) + (kh * 5 + kw) * 4 + c];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) fma4(acc[j][pc], xv[(pc >> 1) + (pc & 1)][j], w4);
                 }
             }
-            RQ[cls][0] = 0.f + u.x; RQ[cls][1] = 0.f + u.y; RQ[cls][2] = 0.f + u.z; RQ[cls][3] = 0.f + u.w;
         }
-        rq_epilogue(a, n, set, g_out, g_out, pos, RQ[0], RQ[1]);
+    }
+    const int h = h0 + row;
+    if (h >= H) return;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int w = w0 + col + 8 * j;
+        if (w >= W) continue;
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++) {
+            const int g_out = g0 + 2 * pi + pr;
+            if (g_out >= G) continue;
+            const float4 r4 = acc[j][pr * 2], q4 = acc[j][pr * 2 + 1];
+            const float R[4] = {0.f + r4.x, 0.f + r4.y, 0.f + r4.z, 0.f + r4.w};
+            const float Q[4] = {0.f + q4.x, 0.f + q4.y, 0.f + q4.z, 0.f + q4.w};
+            rq_epilogue(a, n, set, g_out, g_out, h * W + w, R, Q);
+        }
     }
 }
 
@@ -640,20 +668,25 @@ cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
     }
     const int ny = (a.nchunk + EC_CHUNKS - 1) / EC_CHUNKS, nxy = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
-    const int pair = (long long)nxy * ny * a.N > 2 * 148 ? 1 : 0;  // more than one wave of CTAs (2 per SM): balance them in pairs
-    dim3 grid(nxy, pair ? (ny + 1) / 2 : ny, a.N);
-    cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a, pair);
-    g_launches++;
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (cconv_ec_mma_enabled()) {  // opt-in tensor-core form of the old-term pass (conv_mma.cu): NOT bit-identical to the decoder
+        e = launch_cconv_ec_mma(a, s);
+    } else {
+        const int pair = (long long)nxy * ny * a.N > 2 * 148 ? 1 : 0;  // more than one wave of CTAs (2 per SM): balance them in pairs
+        dim3 grid(nxy, pair ? (ny + 1) / 2 : ny, a.N);
+        cconv_ec_kernel<<<grid, EC_THREADS, EC_SMEM_BYTES, s>>>(a, pair);
+        g_launches++;
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return e;
     const int nqb = (a.cin_g + CB - 1) / CB;
     static const bool rq_tile_off = getenv("LIC360_EC_RQ_GENERIC") != nullptr;
-    if (a.cin_g == 4 && a.cpg4 == 1 && a.G >= 8 && !rq_tile_off) {
+    if (a.cin_g == 4 && a.cpg4 == 1 && a.G >= 8 && a.W % 4 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && !rq_tile_off) {
         static SmemAttr rqt_attr;
-        e = rqt_attr.ensure(cconv_ec_rq_tile_kernel, RQT_SMEM_BYTES);
+        e = rqt_attr.ensure(cconv_ec_rq_tile_kernel, RQ4_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        dim3 grid2(nxy, (a.G + 1) / 2, a.N);
-        cconv_ec_rq_tile_kernel<<<grid2, 256, RQT_SMEM_BYTES, s>>>(a);
+        dim3 grid2(nxy, (a.G + RQ4_G - 1) / RQ4_G, a.N);
+        cconv_ec_rq_tile_kernel<<<grid2, 256, RQ4_SMEM_BYTES, s>>>(a);
     } else if (nqb == 1) {
         const size_t rq_smem = (size_t)2 * TAPS * a.cin_g * sizeof(float4);  // <= 12.8 KB
         dim3 grid2((a.H * a.W + RQ_THREADS - 1) / RQ_THREADS, a.nchunk, a.N);

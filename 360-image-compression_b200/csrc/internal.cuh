@@ -17,6 +17,9 @@ struct StepDesc { int psum, start, len, pad; };
 int fill_conv_args(ConvArgs& a, const float* x, const float* wp, const float* wq, const float* bias, const float* slope,
                    const float* resid, float* out, int N, int Cin, int H, int W, int Cout, int G, int constrain, int nsets);
 cudaError_t launch_cconv_ec(const ConvArgs& a, cudaStream_t s);
+// conv_mma.cu: opt-in (LIC360_EC_MMA=1) tensor-core form of the encoder's old-term pass, mma.sync TF32 with a 3-way split
+bool cconv_ec_mma_enabled();
+cudaError_t launch_cconv_ec_mma(const ConvArgs& a, cudaStream_t s);
 // explicit step (steps == nullptr) or step read on the device from steps[*ctr + ctr_off] (graph replay; grid sized for max_len)
 cudaError_t launch_cconv_dc(const ConvArgs& a, const int32_t* idx_dev, int start, int len, int psum, const StepDesc* steps,
                             const int* ctr, int max_len, cudaStream_t s);

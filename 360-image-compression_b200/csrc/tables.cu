@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(TBL_THREADS) gmm_table_kernel(float* __restric
 // softmax of w logits -> cumulative integer table, entropy_table_cuda.cu:24-50, then fix-up :53-76
 __global__ void __launch_bounds__(TBL_THREADS) entropy_table_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                     int rows, int w, float total) {
-    extern __shared__ float srow[];  // [TBL_THREADS][ns], ns = w + 1 rounded up to an odd stride (row walks are bank-conflict free)
-    const int nt = w + 1, ns = nt | 1;
+    extern __shared__ float srow[];  // [TBL_THREADS][w+1] (an odd row stride was measured slower: the index arithmetic of the copy-out)
+    const int nt = w + 1, ns = nt;
     const int row0 = blockIdx.x * TBL_THREADS;
     const int nrow = min(TBL_THREADS, rows - row0);
     // coalesced load of the logits of this CTA's rows into the (wider) shared rows
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(TBL_THREADS) entropy_table_kernel(const float*
     }
     __syncthreads();
     float* dst = out + (size_t)row0 * nt;
-    for (int e = threadIdx.x; e < nrow * nt; e += TBL_THREADS) dst[e] = srow[(e / nt) * ns + e % nt];
+    for (int e = threadIdx.x; e < nrow * nt; e += TBL_THREADS) dst[e] = srow[e];
 }
 
 // Training NLL and its four cached gradients, entropy_gmm_cuda.cu:36-68 (promotion order kept).
@@ -134,7 +134,7 @@ extern "C" int lic360_entropy_table(const float* in_dev, float* out_dev, int row
     LIC360_CHECK_ARG(nstep >= 1 && nstep <= 64, "nstep must be <= 64 (entropy_table_cuda.cu:13)");
     if (rows <= 0) return LIC360_OK;
     const int grid = (rows + TBL_THREADS - 1) / TBL_THREADS;
-    entropy_table_kernel<<<grid, TBL_THREADS, TBL_THREADS * ((nstep + 1) | 1) * sizeof(float), as_stream(stream)>>>(
+    entropy_table_kernel<<<grid, TBL_THREADS, TBL_THREADS * (nstep + 1) * sizeof(float), as_stream(stream)>>>(
         in_dev, out_dev, rows, nstep, (float)total_region);
     LAUNCH_CHECK();
     return LIC360_OK;

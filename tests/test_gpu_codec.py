@@ -191,3 +191,38 @@ def test_fused_codec_1024x2048_latent():
     code, mup = fused.decode(bi, bc)
     assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
     assert 0 < len(bc) < q.size and 0 < len(bi) < lv.size
+
+
+def test_fused_codec_stress_many_images_in_flight():
+    """Stress of the decoder's cross-CTA data exchange (the code-stream chain reads, with plain L1-allocating loads, values
+    that other CTAs of its cluster stored earlier in the same launch, ordered only by the cluster barrier; the three clusters meet
+    at a global counter): 3 codecs decode concurrently from 3 host threads, 8 different images each, two latent sizes with long
+    diagonals (several items per chain thread).  A single stale or torn read desynchronises the arithmetic decoder, so exact
+    round trips of ~10 million symbols are the check."""
+    import threading
+    import lic360_pipeline as pl
+    errors = []
+    for H, W, nimg in ((64, 128, 8), (96, 160, 4)):
+        params = pl.make_codec_params(DEV, seed=H)
+        codecs = [pl.FusedCodec(params, H=H, W=W) for _ in range(3)]
+        lat = [synthetic_latent(500 + 10 * k + i, H=H, W=W) for k in range(3) for i in range(nimg)]
+
+        def worker(k):
+            try:
+                for i in range(nimg):
+                    q, mask, lv = lat[k * nimg + i]
+                    tq, tm, tl = t(q, DEV), t(mask, DEV), t(lv, DEV)
+                    bi, bc = codecs[k].encode(tq, tm, tl)
+                    code, mup = codecs[k].decode(bi, bc)
+                    if not (np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)):
+                        errors.append((H, W, k, i))
+            except Exception as e:  # noqa: BLE001
+                errors.append((H, W, k, repr(e)))
+
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        del codecs
+    assert not errors, errors
