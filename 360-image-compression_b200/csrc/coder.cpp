@@ -146,16 +146,89 @@ static inline uint32_t gmm_bin(const uint16_t* r, int j) {  // j in 0..8
     return (uint32_t)r[j - 1] | (((uint32_t)(r[7] >> (9 + j - 1)) & 1u) << 16);
 }
 
-int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows) {
-    for (int i = 0; i < nrows; i++) {
-        const uint16_t* r = rows + (size_t)i * 8;
-        if (!((r[7] >> 8) & 1)) continue;  // mask < 0.5: not coded (coder.cpp:79)
-        if (r[7] & 8) { set_error("coder: symbol out of range in packed row %d", i); return LIC360_ERR_CODER; }
-        const int s = r[7] & 7;
-        int rc = ac_update<false>(c, gmm_bin(r, s), gmm_bin(r, s + 1), 65536);
-        if (rc) return rc;
+// Encoder state kept in locals for a whole run of rows (like DecState below): low / high / pending-underflow count in registers,
+// bits through a 64-bit accumulator that is drained 32 bits at a time into a pre-sized buffer (no per-byte vector growth), and
+// the common case "no pending underflow" emits the n matching top bits with one put.  Same bits as ac_update<false>
+// (tests/test_oracle_coder.py pins both against the reference's classes).
+struct EncState {
+    uint32_t low, high;
+    uint64_t underflow;
+    uint64_t acc;
+    int nacc;
+    uint8_t* p;
+    inline void put(uint32_t v, int n) {  // n in 1..32, v < 2^n
+        acc = (acc << n) | v;
+        nacc += n;
+        if (nacc >= 32) {
+            nacc -= 32;
+            const uint32_t w = __builtin_bswap32((uint32_t)(acc >> nacc));
+            memcpy(p, &w, 4);
+            p += 4;
+        }
     }
-    return LIC360_OK;
+    inline bool update(uint32_t t_lo, uint32_t t_hi) {  // total = 65536
+        const uint64_t range = (uint64_t)high - low + 1;
+        uint32_t lo = low + (uint32_t)(((uint64_t)t_lo * range) >> 16), hi = low + (uint32_t)(((uint64_t)t_hi * range) >> 16) - 1;
+        const uint32_t diff = lo ^ hi;
+        if (t_lo == t_hi || diff == 0) return false;
+        const int n = __builtin_clz(diff);
+        if (n > 0) {
+            if (underflow == 0) {
+                put(lo >> (32 - n), n);
+            } else {
+                const uint32_t first = lo >> 31;
+                put(first, 1);
+                for (uint64_t left = underflow; left > 0;) {
+                    const int k = left > 32 ? 32 : (int)left;
+                    put(first ? 0u : (k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1)), k);
+                    left -= k;
+                }
+                underflow = 0;
+                if (n > 1) put((lo >> (32 - n)) & ((1u << (n - 1)) - 1), n - 1);
+            }
+            lo <<= n;
+            hi = (hi << n) | ((1u << n) - 1);
+        }
+        const uint32_t m = (lo & ~hi) << 1;
+        const int k = __builtin_clz(~m | 1u);
+        if (k > 0) {
+            underflow += k;
+            lo = (lo << k) & 0x7FFFFFFFu;
+            hi = ((hi << k) & 0x7FFFFFFFu) | 0x80000000u | ((1u << k) - 1);
+        }
+        low = lo; high = hi;
+        return true;
+    }
+};
+
+// runs `body(EncState&)` over the coder's state with room for `max_bits` more bits in the output buffer
+template <typename F>
+static int with_enc_state(lic360_coder* c, size_t max_bits, F body) {
+    BitWriter& bw = c->bw;
+    const size_t used = bw.bytes.size();
+    bw.bytes.resize(used + max_bits / 8 + 16);
+    EncState e{(uint32_t)c->low, (uint32_t)c->high, c->underflow, bw.acc, bw.nacc, bw.bytes.data() + used};
+    const int rc = body(e);
+    while (e.nacc >= 8) { e.nacc -= 8; *e.p++ = (uint8_t)(e.acc >> e.nacc); }
+    bw.acc = e.acc & ((1ull << e.nacc) - 1);
+    bw.nacc = e.nacc;
+    bw.bytes.resize((size_t)(e.p - bw.bytes.data()));
+    c->low = e.low; c->high = e.high; c->underflow = e.underflow;
+    return rc;
+}
+
+int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows) {
+    // a symbol costs at most 16 bits of information (total 65536) + 1; pending underflow bits were counted when they arose
+    return with_enc_state(c, (size_t)nrows * 34 + (size_t)c->underflow + 64, [&](EncState& e) -> int {
+        for (int i = 0; i < nrows; i++) {
+            const uint16_t* r = rows + (size_t)i * 8;
+            if (!((r[7] >> 8) & 1)) continue;  // mask < 0.5: not coded (coder.cpp:79)
+            if (r[7] & 8) { set_error("coder: symbol out of range in packed row %d", i); return LIC360_ERR_CODER; }
+            const int s = r[7] & 7;
+            if (!e.update(gmm_bin(r, s), gmm_bin(r, s + 1))) { set_error("coder: symbol has zero frequency (row %d)", i); return LIC360_ERR_CODER; }
+        }
+        return LIC360_OK;
+    });
 }
 
 // Decoder state kept in locals for a whole slab; `code` is refilled through the 64-bit accumulator of the bit reader.
