@@ -61,8 +61,14 @@ struct BitReader {
     uint64_t acc = 0;
     int nacc = 0;
     void reset(const uint8_t* data, size_t n) { p = data; len = n; pos = 0; acc = 0; nacc = 0; }
-    inline uint32_t get(int n) {  // n <= 32; past EOF reads zeros (ArithmeticCoder.cpp:131-136)
-        if (n == 0) return 0;
+    inline uint32_t get(int n) {  // 0 <= n <= 32 (n == 0 yields 0); past EOF reads zeros (ArithmeticCoder.cpp:131-136)
+        if (nacc < n && pos + 4 <= len) {  // refill 32 bits at once (nacc < 32 here, so the 64-bit accumulator cannot overflow)
+            uint32_t w;
+            memcpy(&w, p + pos, 4);
+            acc = (acc << 32) | __builtin_bswap32(w);
+            nacc += 32;
+            pos += 4;
+        }
         while (nacc < n) {
             uint64_t b = pos < len ? p[pos] : 0;
             pos++;
@@ -244,12 +250,10 @@ struct DecState {
         uint32_t lo = low + (uint32_t)(pl >> 16), hi = low + (uint32_t)(ph >> 16) - 1;
         const uint32_t diff = lo ^ hi;
         if (pl == ph || diff == 0) return false;
-        const int n = __builtin_clz(diff);
-        if (n > 0) {
-            code = (code << n) | br->get(n);
-            lo <<= n;
-            hi = (hi << n) | ((1u << n) - 1);
-        }
+        const int n = __builtin_clz(diff);  // 0..31 matching top bits; n == 0 flows through the same shifts (no data-dependent branch)
+        code = (code << n) | br->get(n);
+        lo <<= n;
+        hi = (hi << n) | ((1u << n) - 1);
         const uint32_t m = (lo & ~hi) << 1;
         const int k = __builtin_clz(~m | 1u);
         if (k > 0) {
@@ -268,6 +272,9 @@ int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, fl
     int rc = LIC360_OK;
     for (int i = 0; i < nrows; i++) {
         const uint16_t* r = rows + (size_t)i * 8;
+        // the rows were just written by the GPU into pinned memory: every cache line is a miss, and the serial state chain leaves
+        // the hardware prefetcher little to go on -- ask for the lines ahead
+        __builtin_prefetch(r + 8 * 24);
         const uint32_t meta = r[7];
         if (!((meta >> 8) & 1)) { out[i] = fill; continue; }  // coder.cpp:101-102
         const uint64_t range = (uint64_t)st.high - st.low + 1;
