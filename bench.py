@@ -138,7 +138,7 @@ def cpu_arm(steps, warmup, sample_hw=(H, W), budget_s=900.0):
     h, w = sample_hw
     q, mask, lv = synthetic_latent(2024, h, w)
     params = {'code': ops.make_entropy_params(48, 4, 3, 3, 2024, 'cpu'), 'imp': ops.make_entropy_params(1, 144, 49, None, 2025, 'cpu')}
-    codec = cpu_codec.CpuCodec(cpu_codec.params_to_numpy(params))
+    codec = cpu_codec.CpuCodecFast(cpu_codec.params_to_numpy(params))  # channel-last SIMD dot products, same streams (oracle/cpu_codec.py)
     px = (8 * h) * (8 * w) / 1e6
     times, start = [], time.time()
     for it in range(warmup + steps):
@@ -154,8 +154,16 @@ def cpu_arm(steps, warmup, sample_hw=(H, W), budget_s=900.0):
     t = sum(times[-done:]) / done
     from oracle import oracle as O
     return {"value": px / t, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port", "steps_timed": done,
-            "sample": "%dx%d-pixel ERP latent (1,48,%d,%d)+(1,1,%d,%d), encode+decode, OpenMP oracle conv/tables + %s host coder, %.1f s/step"
+            "sample": "%dx%d-pixel ERP latent (1,48,%d,%d)+(1,1,%d,%d), encode+decode, OpenMP channel-last fp32 conv + oracle tables + %s host coder, %.1f s/step"
                       % (8 * h, 8 * w, h, w, h // 2, w // 2, "reference" if O.have_ref_coder() else "restated", t)}, t
+
+
+def workload_config(h=H, w=W):
+    """`config` of the JSON line, identical for both arms (the reference arm times the same workload on the host cores)"""
+    return {"workload": "configs[1]: 512x1024 ERP entropy encode+decode (importance + code stream), batch 1 per GPU, model-idx-3 shape, seeded random-init weights"
+                        + ("" if (h, w) == (H, W) else " -- REDUCED sample, latent %dx%d" % (h, w)),
+            "latent": [1, 48, h, w], "images_per_gpu_per_step": 1, "l2": "256 MB buffer written between iterations (L2 flush)",
+            "parallelism": "image-sharded, no collective"}
 
 
 def emit(line, real_stdout):
@@ -190,18 +198,16 @@ def main():
         if world > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
             if os.environ.get("OMP_NUM_THREADS", "1") == "1":
                 os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # ~3000 short parallel regions per image: do not burn the cores between them
         # the SAME config and the same K / W as the b200 arm: one full 512x1024 image per step (about 20 s of CPU work per step on the
         # box's host cores; LIC360_BENCH_REF_SAMPLE=h,w shrinks the latent for a quick look, and says so in `config`)
         steps, ref_warm = max(1, args.steps), max(0, args.warmup)
         hw = tuple(int(v) for v in os.environ.get("LIC360_BENCH_REF_SAMPLE", "%d,%d" % (H, W)).split(","))
         cb, t = cpu_arm(steps, ref_warm, hw)
-        full = hw == (H, W)
         line = {"impl": "reference", "metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": cb["value"], "unit": "Mpx/s",
                 "n_gpus": args.gpus, "steps": cb["steps_timed"], "warmup": ref_warm, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[1]: 512x1024 ERP entropy encode+decode (importance + code stream), batch 1 per GPU, model-idx-3 shape, seeded random-init weights"
-                                       + ("" if full else " -- REDUCED CPU sample: " + cb["sample"]),
-                           "latent": [1, 48, hw[0], hw[1]], "images_per_gpu_per_step": 1, "cpu_sample": cb["sample"]},
+                "config": workload_config(*hw),
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line, real_stdout)
@@ -404,9 +410,7 @@ def main():
     line = {"metric": "ERP Mpx/s encode+decode (entropy path, model-idx 3 shape)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 512x1024 ERP entropy encode+decode (importance + code stream), batch 1 per GPU, model-idx-3 shape, seeded random-init weights",
-                       "latent": [1, 48, H, W], "images_per_gpu_per_step": 1, "l2": "256 MB buffer written between iterations (L2 flush)",
-                       "parallelism": "image-sharded, no collective"},
+            "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
                     "d2h_bytes_per_step": int(2 * tq.numel() * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline_chain, "roofline_data_mover": roofline, "flop_view": flop_view,

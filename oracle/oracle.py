@@ -80,6 +80,50 @@ def cconv_dc_step(x, w, b, slope, out, G, constrain, nsets, idx, plan, psum):
     return out
 
 
+# ---- CPU-baseline form (channel-last, contiguous masked dot products; bench.py's cpu arm only)
+_pwc = _sig("orc_pack_weights_cl", [_P, _P, _I, _I, _I, _I])
+_ecc = _sig("orc_cconv_ec_cl", [_P] * 6 + [_I] * 9)
+_dcc = _sig("orc_cconv_dc_step_cl", [_P] * 6 + [_I] * 9 + [_P, _P, _I])
+_tec = _sig("orc_tile_extract_cl", [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I], _I)
+
+
+def pack_weights_cl(w, nsets):
+    """(nsets, Cout, Cin, k, k) or (Cout, Cin, k, k) -> (nsets, Cout, k*k, Cin)"""
+    w = _f(w)
+    Cout, Cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
+    wt = np.zeros((nsets, Cout, k * k, Cin), np.float32)
+    _pwc(_p(w), _p(wt), nsets, Cout, Cin, k)
+    return wt
+
+
+def cconv_ec_cl(x, wt, b, slope, resid, G, constrain):
+    """x (N,H,W,Cin) channel-last -> (N,H,W,Cout)"""
+    x, b = _f(x), _f(b)
+    slope = None if slope is None else _f(slope)
+    resid = None if resid is None else _f(resid)
+    N, H, W, Cin = x.shape
+    nsets, Cout, kk, _ = wt.shape
+    out = np.zeros((N, H, W, Cout), np.float32)
+    _ecc(_p(x), _p(wt), _p(b), _p(slope), _p(resid), _p(out), N, Cin, H, W, Cout, G, int(round(kk ** 0.5)), constrain, nsets)
+    return out
+
+
+def cconv_dc_step_cl(x, wt, b, slope, resid, out, G, constrain, idx, plan, psum):
+    b = _f(b)
+    slope = None if slope is None else _f(slope)
+    N, H, W, Cin = x.shape
+    nsets, Cout, kk, _ = wt.shape
+    assert x.dtype == np.float32 and x.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
+    _dcc(_p(x), _p(wt), _p(b), _p(slope), _p(resid), _p(out), N, Cin, H, W, Cout, G, int(round(kk ** 0.5)), constrain, nsets,
+         _p(idx), _p(plan), psum)
+    return out
+
+
+def tile_extract_cl(x, out, G, idx, plan, psum):
+    N, H, W, C = x.shape
+    return _tec(_p(x), _p(out), N, C, H, W, G, _p(idx), _p(plan), psum)
+
+
 # ------------------------------------------------------------------------------------------------ tile ops
 _te = _sig("orc_tile_extract", [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I], _I)
 _teb = _sig("orc_tile_extract_batch", [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I], _I)
