@@ -58,3 +58,30 @@ def test_sphere_operator_alias(lib_built):
     import sphere_operator  # train/model_zoo.py:3-12
     import lic360_operator
     assert sphere_operator.CconvDc is lic360_operator.CconvDc
+
+
+def test_reference_python_imports_on_the_mirror(lib_built):
+    """No GPU needed: the reference's own `lic360_operator` package, `test/model_zoo.py` and `test/lic360_demo.py` import on top of this
+    repo's `lic360` mirror and their codec-form modules construct (tools/run_reference_scripts.py does the rest on the GPU box)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    have = any(os.path.exists(os.path.join(r, "test", "lic360_demo.py")) for r in ("/root/reference", os.path.join(root, "baseline", "_ref")))
+    if not have:
+        pytest.skip("reference Python not available (make -f oracle/Makefile.ref pyref)")
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import run_reference_scripts as h
+ref = h.bind_backend("b200")
+import lic360, lic360_operator, lic360_demo as demo
+assert "360-image-compression_b200" in lic360.__file__ and lic360_operator.__file__.startswith(ref) and demo.__file__.startswith(ref)
+from lic360_operator import CconvEcBatch, CconvDcBatch, TileAdd, TileExtractBatch, TileInput, EntropyBatchGmmTable, MultiProject
+m = CconvEcBatch(48, 1, 4, 5, 3, False, True, device=0)
+assert sorted(m.state_dict()) == ["bias", "relu", "weight"] and tuple(m.weight.shape) == (3, 192, 48, 5, 5)
+CconvDcBatch(48, 4, 4, 5, 3, True, True, device=0); TileAdd(48, device=0); TileExtractBatch(48, True, device=0)
+TileInput(48, -3.5, 1, 3, device=0); EntropyBatchGmmTable(8, 3.5, 3, 65536, device=0); MultiProject(171, 256, 0.5, False, 0)
+print("ok")
+''' % os.path.join(root, "tools")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
