@@ -67,6 +67,7 @@ struct NetDesc {
     uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
     float* syms_host = nullptr;         // mapped pinned: decoded symbols of one step
     int row_bytes = 16;                 // packed row size (16 B code stream, 128 B importance stream)
+    bool tagged = false;                // decode: the step's rows carry a publication tag and are validated row by row (no fence + flag)
     double t_host_coder = 0, t_gpu_wait = 0, t_done = 0;
     lic360_coder* coder = nullptr;
     char err[256] = {0};                // error text of a worker thread (set_error is thread-local)
@@ -502,6 +503,10 @@ static int launch_step(lic360_codec* c, NetDesc& n, bool is_code, cudaStream_t s
     if (n.nflags > 64) { set_error("codec: %d chain CTAs exceed the 64 host flags", n.nflags); return LIC360_ERR_ARG; }
     const bool rtail = fused_rows && is_code && n.wf.chain4 && !getenv("LIC360_WF_PREV_KERNEL");
     rows.rtail = rtail ? 1 : 0;
+    // code stream: every 16-byte row is published by its own tag (step % 15 + 1 in the meta word; 0 = never written); the host decodes row i as soon as
+    // it has arrived -- no system fence and no flag write behind the rows, and the PCIe flight of the later rows overlaps the decoding
+    n.tagged = fused_rows && is_code && n.wf.chain4 && !getenv("LIC360_WF_ROWS_FLAGS");
+    rows.tagged = n.tagged ? 1 : 0;
     LIC360_CUDA(wf_launch_chain(n.wf, s, fused_rows ? &rows : nullptr));
     WF_DEBUG_SYNC("chain kernel");
     if (ev) LIC360_CUDA(cudaEventRecord(ev[3], s));
@@ -841,6 +846,24 @@ static int wait_rows(lic360_codec* c, NetDesc& n, int p) {
     return LIC360_OK;
 }
 
+// called by the tagged row decoder every few thousand polls of a row that has not arrived: the same give-up conditions as wait_rows
+struct StallCtx { lic360_codec* c; NetDesc* n; int p; clk::time_point t0; };
+static int rows_stalled(void* vp) {
+    StallCtx* x = static_cast<StallCtx*>(vp);
+    NetDesc& n = *x->n;
+    if (x->c->abort_flag.load()) { set_error("codec: aborted (the other stream failed)"); return LIC360_ERR_CUDA; }
+    for (int i = 0; i < n.nflags; i++)
+        if (__atomic_load_n(n.flag_host + i, __ATOMIC_ACQUIRE) < 0) {
+            set_error("codec: step %d: a chain cluster gave up waiting for the other nets' clusters (too many decodes in flight on this device?)", x->p);
+            return LIC360_ERR_CUDA;
+        }
+    const cudaError_t e = cudaStreamQuery(n.stream);
+    if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("codec: step %d failed -> %s", x->p, cudaGetErrorString(e)); return LIC360_ERR_CUDA; }
+    if (ms_since(x->t0) > 20000.) { set_error("codec: step %d timed out waiting for its rows", x->p); return LIC360_ERR_CUDA; }
+    sched_yield();
+    return 0;
+}
+
 static int final_scatter(lic360_codec* c, NetDesc& n, bool is_code) {
     // scatter the symbols of the last step (the final TileInput of lic360_demo.py:236,285)
     const WfNetDev& w = n.wf.dev;
@@ -863,6 +886,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaStream_t s = n.stream;
     int rc = LIC360_OK;
     for (int i = 0; i < 64; i++) n.flag_host[i] = 0;
+    memset(n.rows_step_host, 0, (size_t)n.max_len * n.row_bytes);  // publication tags of a previous decode must not match step 0
     // Launch-ahead (experiment, LIC360_WF_LAUNCH_AHEAD=1; measured ~1 ms SLOWER per 512x1024 decode than launching each step's
     // graph when its symbols are ready, so it is off by default): while the GPU works on step p the host already enqueues
     // [wait until *go >= p+1][graph of step p+1]; once the symbols of step p are decoded (and, for the code stream, the importance
@@ -920,8 +944,10 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
                     wait_value = nullptr;  // not supported here: plain launch per step
                 }
             }
-            rc = wait_rows(c, n, p);
-            if (rc) return rc;
+            if (!n.tagged) {
+                rc = wait_rows(c, n, p);
+                if (rc) return rc;
+            }
         } else {
             if (is_code) { rc = wait_levels(p); if (rc) return rc; }
             rc = launch_step(c, n, is_code, s, s, n.ev_prof);
@@ -935,8 +961,22 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
         if (!is_code) c->imp_ready.store(p, std::memory_order_release);  // the scatter of this step wrote diagonal p-1
         auto th = clk::now();
         const int len = n.steps[p].len;
-        rc = is_code ? coder_decode_packed_gmm(n.coder, n.rows_step_host, len, n.syms_host)
-                     : coder_decode_packed_imp(n.coder, n.rows_step_host, len, n.syms_host);
+        if (is_code && n.tagged) {
+            StallCtx sc{c, &n, p, clk::now()};
+            // time until the first row is there = waiting for the GPU; the rest of the call decodes while the later rows arrive
+            for (unsigned spins = 1; ((__atomic_load_n(n.rows_step_host + 7, __ATOMIC_ACQUIRE) >> 4) & 15) != (unsigned)(p % 15 + 1); spins++) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                if ((spins & 0x3FFF) == 0) { rc = rows_stalled(&sc); if (rc) return rc; }
+            }
+            n.t_gpu_wait += ms_since(th);
+            th = clk::now();
+            rc = coder_decode_packed_gmm_tagged(n.coder, n.rows_step_host, len, n.syms_host, p % 15 + 1, rows_stalled, &sc);
+        } else {
+            rc = is_code ? coder_decode_packed_gmm(n.coder, n.rows_step_host, len, n.syms_host)
+                         : coder_decode_packed_imp(n.coder, n.rows_step_host, len, n.syms_host);
+        }
         n.t_host_coder += ms_since(th);
         if (rc) return rc;
         if (ahead) {

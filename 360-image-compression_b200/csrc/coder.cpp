@@ -266,12 +266,27 @@ struct DecState {
     }
 };
 
-int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, float* out) {
+template <bool kTagged>
+static int decode_packed_gmm_impl(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx) {
     DecState st{(uint32_t)c->low, (uint32_t)c->high, (uint32_t)c->code, &c->br};
     const float fill = c->fill;
     int rc = LIC360_OK;
     for (int i = 0; i < nrows; i++) {
         const uint16_t* r = rows + (size_t)i * 8;
+        if (kTagged) {
+            // the row is one 16-byte device store: once the meta word shows this step's tag the whole row is there (acquire: the
+            // loads of the bins below must not be satisfied before it)
+            unsigned spins = 0;
+            while (((__atomic_load_n(r + 7, __ATOMIC_ACQUIRE) >> 4) & 15) != (unsigned)(tag & 15)) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                if ((++spins & 0x3FFF) == 0 && stalled) {
+                    const int give_up = stalled(ctx);
+                    if (give_up) { c->low = st.low; c->high = st.high; c->code = st.code; return give_up; }
+                }
+            }
+        }
         // the rows were just written by the GPU into pinned memory: every cache line is a miss, and the serial state chain leaves
         // the hardware prefetcher little to go on -- ask for the lines ahead
         __builtin_prefetch(r + 8 * 24);
@@ -298,6 +313,14 @@ int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, fl
     }
     c->low = st.low; c->high = st.high; c->code = st.code;
     return rc;
+}
+
+int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, float* out) {
+    return decode_packed_gmm_impl<false>(c, rows, nrows, out, 0, nullptr, nullptr);
+}
+
+int coder_decode_packed_gmm_tagged(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx) {
+    return decode_packed_gmm_impl<true>(c, rows, nrows, out, tag, stalled, ctx);
 }
 
 static inline uint32_t imp_bin(const uint16_t* r, int j) {  // j in 0..49

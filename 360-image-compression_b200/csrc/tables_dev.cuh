@@ -137,7 +137,9 @@ __device__ __forceinline__ void entropy_row49_warp(float v0, float v1, float* o,
 // packed code-stream row (coder_internal.h): 7 x u16 low words of T[1..7] + meta = sym | bad << 3 | mask << 8 | overflow bits << 9
 // bad: the symbol is outside 0..7 (sym >= 8 or negative); the host encoder reports it like the per-op path does ("symbol out
 // of range") instead of coding a wrapped, decodable but wrong symbol
-__device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst) {
+// tag (4 bits, meta bits 4..7): publication tag of the decoder's per-step rows (wavefront.cu): a row is ONE aligned 16-byte store, so
+// the host can validate every row by its tag instead of waiting for a fence + flag behind all of them
+__device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbit, uint16_t* dst, int tag = 0) {
     uint32_t ovf = 0;
     uint16_t w[8];
 #pragma unroll
@@ -146,7 +148,7 @@ __device__ __forceinline__ void pack_gmm_row(const float* o, int sym, int maskbi
         w[j - 1] = (uint16_t)(v & 0xFFFF);
         ovf |= ((v >> 16) & 1u) << (j - 1);
     }
-    w[7] = (uint16_t)((sym & 7) | ((unsigned)sym > 7u ? 8 : 0) | (maskbit << 8) | (ovf << 9));
+    w[7] = (uint16_t)((sym & 7) | ((unsigned)sym > 7u ? 8 : 0) | ((tag & 15) << 4) | (maskbit << 8) | (ovf << 9));
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(w);
 }
 

@@ -699,8 +699,12 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
         if (live && j == 0) {
             fixup_row(o, 8, true);
             const int lvl = (int)(rows.levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
-            pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows.rows + (size_t)li * 8);
+            pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows.rows + (size_t)li * 8, rows.tagged ? psum % 15 + 1 : 0);
         }
+    }
+    if (rows.tagged) {  // self-validating rows: no fence, no flag; the host decodes row i as soon as row i carries this step's tag
+        if (tid == 0) WF_TRACE_MAX(net.G, psum, WF_TR_ROWS1);
+        return;
     }
     // every CTA raises its own host flag once its rows are on their way (the host waits for all of them): no second
     // device-wide counter round and no second system fence between the last row and the flag

@@ -51,6 +51,7 @@ struct WfRows {
     float s2;
     int enabled;
     int rtail;            // the chain kernel also evaluates the previous-wavefront terms of the NEXT step (layers 1..11) behind the rows
+    int tagged;           // rows carry the publication tag step % 15 + 1 and are NOT followed by a system fence + flag: the host validates row by row
 };
 
 struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer, box {40 h, 9 d, 4 c}

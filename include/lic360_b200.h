@@ -196,7 +196,8 @@ long lic360_coder_get_bytes(lic360_coder* c, uint8_t* out, long cap);
 int lic360_coder_start_decoder_mem(lic360_coder* c, const uint8_t* bytes, long n);
 /* the slab loops of coder.cpp:62-114 (encodes_mask / decodes_mask / encodes / decodes) over PACKED CDF rows, the format the fused
  * codec's kernels write into pinned memory (same integers as the int32 tables, end points 0 and 65536 dropped):
- *   kind 0, code stream      :  8 x u16 per symbol = T[1..7] low words, meta = symbol(3 bits) | mask << 8 | bit 16 of T[1..7] << 9
+ *   kind 0, code stream      :  8 x u16 per symbol = T[1..7] low words, meta = symbol(3 bits) | out-of-range << 3 | publication tag << 4
+ *                               | mask << 8 | bit 16 of T[1..7] << 9  (the tag is only used between the decoder's kernels and its host loop)
  *   kind 1, importance stream: 64 x u16 per symbol = T[1..48] low words, [48] = symbol, [49..51] = bit 16 of T[1..48]
  * decode writes the symbols (fill_value where the mask bit is 0) to out[nrows] */
 int lic360_coder_encode_rows(lic360_coder* c, const uint16_t* rows, int nrows, int kind);
