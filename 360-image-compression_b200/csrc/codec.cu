@@ -61,11 +61,15 @@ struct NetDesc {
     int* sync_dev = nullptr;            // code stream: monotone cross-cluster counter of the chain kernel's rows phase
     int* flag_host = nullptr;           // mapped pinned: step + 1 once the rows of a step are in rows_step_host
     int nflags = 1;                     // host flags the rows producer raises (one per CTA of the fused code-stream chain)
-    int* go_host = nullptr;             // mapped pinned: the stream may run step p once this is >= p (launch-ahead, decode_stream)
+    int* go_host = nullptr;             // mapped pinned: the stream may run step p once this is >= p (launch-ahead / persistent decode)
+    int* go_dev = nullptr;              // persistent decode: CTA 0's republished go / abort decision
+    int* old_done_dev = nullptr;        // persistent decode: old-term sums of steps < this are complete
+    int* scat_done_dev = nullptr;       // persistent decode, one per net: symbols of steps < this are in the net's input frame
     uint16_t* rows_dev = nullptr;       // encode: all rows of the stream
     uint16_t* rows_host = nullptr;      // pinned
     uint16_t* rows_step_host = nullptr; // mapped pinned: rows of one decode step
     float* syms_host = nullptr;         // mapped pinned: decoded symbols of one step
+    std::vector<float> step_wait_us, step_decode_us, step_levels_us;  // debug timeline (LIC360_WF_TRACE_FILE): host time per step waiting for rows / decoding
     int row_bytes = 16;                 // packed row size (16 B code stream, 128 B importance stream)
     bool tagged = false;                // decode: the step's rows carry a publication tag and are validated row by row (no fence + flag)
     double t_host_coder = 0, t_gpu_wait = 0, t_done = 0;
@@ -612,6 +616,9 @@ static int ctx_alloc(NetDesc& n, int row_bytes, float fill, int prio_hi, int pri
     LIC360_CUDA(cudaMalloc(&n.done_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.arrived_dev, sizeof(int)));
     LIC360_CUDA(cudaMalloc(&n.sync_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.go_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.old_done_dev, sizeof(int)));
+    LIC360_CUDA(cudaMalloc(&n.scat_done_dev, 4 * sizeof(int)));
     LIC360_CUDA(cudaHostAlloc(&n.flag_host, 64 * sizeof(int), cudaHostAllocMapped));
     LIC360_CUDA(cudaHostAlloc(&n.go_host, 64, cudaHostAllocMapped));
     *n.go_host = 0;
@@ -628,7 +635,8 @@ static int ctx_buffers(NetDesc& n) {
 }
 
 static void ctx_free(NetDesc& n) {
-    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.arrived_dev); cudaFree(n.sync_dev); cudaFreeHost(n.flag_host); cudaFreeHost(n.go_host);
+    cudaFree(n.ctr_dev); cudaFree(n.done_dev); cudaFree(n.arrived_dev); cudaFree(n.sync_dev); cudaFree(n.go_dev); cudaFree(n.old_done_dev); cudaFree(n.scat_done_dev);
+    cudaFreeHost(n.flag_host); cudaFreeHost(n.go_host);
     cudaFree(n.rows_dev); cudaFreeHost(n.rows_host); cudaFreeHost(n.rows_step_host); cudaFreeHost(n.syms_host);
     if (n.ev_fork) cudaEventDestroy(n.ev_fork);
     if (n.ev_join) cudaEventDestroy(n.ev_join);
@@ -879,10 +887,111 @@ static int final_scatter(lic360_codec* c, NetDesc& n, bool is_code) {
     return LIC360_OK;
 }
 
+// code stream: the importance levels step p needs are decoded (cells on importance diagonals <= min(p, H+W-2)/2), published by the
+// importance loop running concurrently on another host thread and CUDA stream
+static int wait_levels(lic360_codec* c, const NetDesc& n, int p) {
+    const int need = std::min(p, n.H + n.W - 2) / 2 + 1;
+    const auto t0 = clk::now();
+    for (unsigned spins = 1; c->imp_ready.load(std::memory_order_acquire) < need; spins++) {
+        if ((spins & 0xFFF) == 0 && (c->abort_flag.load() || ms_since(t0) > 20000.)) {
+            set_error("codec: the importance stream did not deliver the levels the code stream needs");
+            return LIC360_ERR_CODER;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x1F) == 0) sched_yield();
+    }
+    return LIC360_OK;
+}
+
+// stops a persistent chain kernel at its next step boundary, whatever way the host loop is left (after a normal decode the kernel has
+// already exited and the store is harmless)
+struct PersistStop {  // every exit path: the chain kernel stops at its next step boundary
+    int* go;
+    ~PersistStop() { __atomic_store_n(go, WF_GO_ABORT, __ATOMIC_RELEASE); }
+};
+
+// Low-latency decode of the code stream (mode 2): ONE launch of the chain kernel walks all wavefront steps (wavefront.cu, WfPersist).
+// Per step the host only (1) stores the go flag -- the symbols of the previous step are in mapped memory by then --, (2) enqueues an
+// old-term kernel on the low-priority side stream, (3) decodes the rows as they arrive.  Against the graph replay per step this
+// takes the graph launch, the scatter kernel and the chain kernel's prologue off the critical path; the price is that the chain's 24
+// SMs stay occupied for the whole decode (fine for one image at a time, the wrong trade with several in flight).
+static int decode_stream_persistent(lic360_codec* c, NetDesc& n) {
+    cudaStream_t s = n.stream, side = n.side;
+    for (int i = 0; i < 64; i++) n.flag_host[i] = 0;
+    memset(n.rows_step_host, 0, (size_t)n.max_len * n.row_bytes);
+    memset(n.syms_host, 0, (size_t)n.max_len * sizeof(float));  // tag 0 = not published
+    __atomic_store_n(n.go_host, -1, __ATOMIC_RELEASE);
+    PersistStop stop{n.go_host};
+    n.t_host_coder = 0; n.t_gpu_wait = 0;
+    const bool trace_file = getenv("LIC360_WF_TRACE_FILE") != nullptr;
+    n.step_wait_us.clear(); n.step_decode_us.clear(); n.step_levels_us.clear();
+    for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
+    LIC360_CUDA(wf_clear(n.wf, s));
+    LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0xFF, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.arrived_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.sync_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.go_dev, 0xFF, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.old_done_dev, 0, sizeof(int), s));
+    LIC360_CUDA(cudaMemsetAsync(n.scat_done_dev, 0, 4 * sizeof(int), s));
+    LIC360_CUDA(cudaEventRecord(n.ev_fork, s));
+    LIC360_CUDA(cudaStreamWaitEvent(side, n.ev_fork, 0));
+    LIC360_CUDA(wf_launch_old(n.wf, 0, side, false, 0, n.old_done_dev, n.scat_done_dev));  // old terms of step 0 (all zero; keeps the protocol uniform)
+    WfRows rows;
+    memset(&rows, 0, sizeof(rows));
+    rows.rows = n.rows_step_host; rows.levels = c->levels_dev; rows.done = n.done_dev; rows.flag = n.flag_host;
+    rows.sync = n.sync_dev; rows.s2 = (float)(1. / sqrt(2.0)); rows.enabled = 1; rows.rtail = 1; rows.tagged = 1;
+    n.tagged = true;
+    n.nflags = n.wf.dev.nsets * n.wf.cluster;
+    if (n.nflags > 64) { set_error("codec: %d chain CTAs exceed the 64 host flags", n.nflags); return LIC360_ERR_ARG; }
+    WfPersist ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.syms = n.syms_host; ps.go_host = n.go_host; ps.go_dev = n.go_dev; ps.old_done = n.old_done_dev; ps.ctr = n.ctr_dev; ps.scat_done = n.scat_done_dev;
+    ps.bias = -3.5f; ps.scale = 1.0f;
+    LIC360_CUDA(wf_launch_chain(n.wf, s, &rows, &ps));
+    int rc = LIC360_OK;
+    for (int p = 0; p < n.nsteps; p++) {
+        auto tw = clk::now();
+        rc = wait_levels(c, n, p);
+        if (rc) return rc;
+        if (trace_file) n.step_levels_us.push_back((float)(ms_since(tw) * 1e3));
+        __atomic_store_n(n.go_host, p, __ATOMIC_RELEASE);  // step p may run: the symbols of step p - 1 are in syms_host
+        // old terms of step p + 1: they read wavefronts <= p - 1, complete now; enqueued behind the go so that the launch costs no time on
+        // the critical path (the GPU is busy with step p for the next ~60 us)
+        if (p + 1 < n.nsteps) LIC360_CUDA(wf_launch_old(n.wf, 0, side, false, p + 1, n.old_done_dev, n.scat_done_dev));
+        StallCtx sc{c, &n, p, clk::now()};
+        for (unsigned spins = 1; ((__atomic_load_n(n.rows_step_host + 7, __ATOMIC_ACQUIRE) >> 4) & 15) != (unsigned)(p % 15 + 1); spins++) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0x3FFF) == 0) { rc = rows_stalled(&sc); if (rc) return rc; }
+        }
+        n.t_gpu_wait += ms_since(tw);
+        if (trace_file) n.step_wait_us.push_back((float)(ms_since(tw) * 1e3));
+        auto th = clk::now();
+        rc = coder_decode_packed_gmm_tagged(n.coder, n.rows_step_host, n.steps[p].len, n.syms_host, p % 15 + 1, rows_stalled, &sc,
+                                            p + 1 < n.nsteps ? (unsigned)(p % 15 + 1) : 0u);  // symbol words tagged too: the chain kernel polls
+                                            // them one by one (not the last step's: the final scatter reads plain floats)
+        n.t_host_coder += ms_since(th);
+        if (trace_file) n.step_decode_us.push_back((float)(ms_since(th) * 1e3));
+        if (rc) return rc;
+    }
+    LIC360_CUDA(cudaEventRecord(n.ev_join, side));
+    LIC360_CUDA(cudaStreamWaitEvent(s, n.ev_join, 0));
+    return final_scatter(c, n, true);  // behind the chain kernel in stream order; the device step counter is nsteps - 1
+}
+
 // The wavefront loop of one bitstream.  is_code: before step p the importance levels of every 2x2 cell the slab touches
 // must be decoded (cells on importance diagonals <= min(p, H+W-2)/2): the loop waits on c->imp_ready, which the
 // importance loop (running concurrently on another host thread and CUDA stream) publishes.
+static bool persistent_ok(const lic360_codec* c, const NetDesc& n) {
+    return c->mode == 2 && n.wf.chain4 && n.wf.r0_inline && n.wf.old2 && !getenv("LIC360_WF_ROWS_KERNEL") && !getenv("LIC360_WF_PREV_KERNEL");
+}
+
 static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
+    if (is_code && persistent_ok(c, n)) return decode_stream_persistent(c, n);
     cudaStream_t s = n.stream;
     int rc = LIC360_OK;
     for (int i = 0; i < 64; i++) n.flag_host[i] = 0;
@@ -892,7 +1001,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     // [wait until *go >= p+1][graph of step p+1]; once the symbols of step p are decoded (and, for the code stream, the importance
     // levels step p+1 needs are there) one store to the mapped flag lets the stream's front end start the step.  The wait is a
     // stream memory operation (no kernel spins); GoRelease un-parks the stream on every exit path.
-    StreamWaitValue32Fn wait_value = c->mode == 0 ? stream_wait_value_fn() : nullptr;
+    StreamWaitValue32Fn wait_value = c->mode != 1 ? stream_wait_value_fn() : nullptr;
     CUdeviceptr go_dev = 0;
     if (wait_value) {
         void* dp = nullptr;
@@ -902,6 +1011,8 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     __atomic_store_n(n.go_host, 0, __ATOMIC_RELEASE);
     GoRelease go_release{n.go_host};
     n.t_host_coder = 0; n.t_gpu_wait = 0;
+    const bool trace_file = getenv("LIC360_WF_TRACE_FILE") != nullptr;
+    n.step_wait_us.clear(); n.step_decode_us.clear(); n.step_levels_us.clear();
     LIC360_CUDA(wf_clear(n.wf, s));
     LIC360_CUDA(cudaMemsetAsync(n.ctr_dev, 0xFF, sizeof(int), s));  // -1: the scatter kernel of step p makes it p
     LIC360_CUDA(cudaMemsetAsync(n.done_dev, 0, sizeof(int), s));
@@ -910,27 +1021,13 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
     LIC360_CUDA(wf_launch_old(n.wf, 1, s));  // old terms of step 0 = counter (-1) + 1 (all zero, but it keeps the schedule uniform)
     if (getenv("LIC360_DEBUG_SYNC")) LIC360_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 5; i++) n.t_kernel[i] = 0;
-    auto wait_levels = [&](int p) -> int {  // code stream: the importance levels step p needs are decoded
-        const int need = std::min(p, n.H + n.W - 2) / 2 + 1;
-        const auto t0 = clk::now();
-        for (unsigned spins = 1; c->imp_ready.load(std::memory_order_acquire) < need; spins++) {
-            if ((spins & 0xFFF) == 0 && (c->abort_flag.load() || ms_since(t0) > 20000.)) {
-                set_error("codec: the importance stream did not deliver the levels the code stream needs");
-                return LIC360_ERR_CODER;
-            }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-            if ((spins & 0x1F) == 0) sched_yield();
-        }
-        return LIC360_OK;
-    };
     bool ahead = false;  // the graph of the current step is already enqueued (behind its go flag)
     for (int p = 0; p < n.nsteps; p++) {
         auto tw = clk::now();
-        if (c->mode == 0) {
+        if (c->mode != 1) {
             if (!ahead) {
-                if (is_code) { rc = wait_levels(p); if (rc) return rc; }
+                if (is_code) { rc = wait_levels(c, n, p); if (rc) return rc; }
+                if (trace_file && is_code) n.step_levels_us.push_back((float)(ms_since(tw) * 1e3));
                 LIC360_CUDA(cudaGraphLaunch(n.graph, s));
                 g_launches += n.graph_nodes;
             }
@@ -949,7 +1046,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
                 if (rc) return rc;
             }
         } else {
-            if (is_code) { rc = wait_levels(p); if (rc) return rc; }
+            if (is_code) { rc = wait_levels(c, n, p); if (rc) return rc; }
             rc = launch_step(c, n, is_code, s, s, n.ev_prof);
             if (rc) return rc;
             LIC360_CUDA(cudaStreamSynchronize(s));
@@ -971,6 +1068,7 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
                 if ((spins & 0x3FFF) == 0) { rc = rows_stalled(&sc); if (rc) return rc; }
             }
             n.t_gpu_wait += ms_since(th);
+            if (trace_file) n.step_wait_us.push_back((float)(ms_since(tw) * 1e3));
             th = clk::now();
             rc = coder_decode_packed_gmm_tagged(n.coder, n.rows_step_host, len, n.syms_host, p % 15 + 1, rows_stalled, &sc);
         } else {
@@ -978,9 +1076,10 @@ static int decode_stream(lic360_codec* c, NetDesc& n, bool is_code) {
                          : coder_decode_packed_imp(n.coder, n.rows_step_host, len, n.syms_host);
         }
         n.t_host_coder += ms_since(th);
+        if (trace_file && is_code && n.tagged) n.step_decode_us.push_back((float)(ms_since(th) * 1e3));
         if (rc) return rc;
         if (ahead) {
-            if (is_code) { rc = wait_levels(p + 1); if (rc) return rc; }
+            if (is_code) { rc = wait_levels(c, n, p + 1); if (rc) return rc; }
             __atomic_store_n(n.go_host, p + 1, __ATOMIC_RELEASE);  // symbols of step p are in syms_host: step p+1 may run
         }
     }
@@ -1014,15 +1113,15 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         std::vector<unsigned long long> init((size_t)tr_steps * WF_TR_SLOTS + 64, 0ull);  // + per-layer phase sums of the G = 1 chain
         for (int p = 0; p < tr_steps; p++)
             for (int k = 0; k < WF_TR_SLOTS; k++)
-                init[(size_t)p * WF_TR_SLOTS + k] = (k == WF_TR_CHAIN1 || k == WF_TR_ROWS1 || k == WF_TR_OLD1) ? 0ull : ~0ull;
+                init[(size_t)p * WF_TR_SLOTS + k] = (k == WF_TR_CHAIN1 || k == WF_TR_ROWS1 || k == WF_TR_OLD1 || k == WF_TR_TAIL1) ? 0ull : ~0ull;
         LIC360_CUDA(cudaMalloc(&trace_dev, init.size() * 8));
         LIC360_CUDA(cudaMemcpy(trace_dev, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
         wf_trace_set(trace_dev, tr_sel);
         codec_trace_set(trace_dev, tr_sel);
     }
-    if (c->mode == 0) {  // both step graphs exist before the second host thread starts
+    if (c->mode != 1) {  // both step graphs exist before the second host thread starts (the persistent code stream needs none)
         rc = build_step_graph(c, c->imp, false);
-        if (rc == LIC360_OK) rc = build_step_graph(c, c->code, true);
+        if (rc == LIC360_OK && !persistent_ok(c, c->code)) rc = build_step_graph(c, c->code, true);
         if (rc) return rc;
     }
     lic360_coder_start_decoder_mem(c->imp.coder, imp_bytes, n_imp);
@@ -1040,7 +1139,7 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         }
         c->t_imp = ms_since(t0);
     };
-    if (c->mode == 0) {
+    if (c->mode != 1) {
         ChainSlot slot(c->device, c->chain_cap);  // queues here when the device already runs as many decodes as it can hold
         c->imp_worker.submit(imp_loop);
         rc = decode_stream(c, c->code, true);
@@ -1069,7 +1168,7 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         wf_trace_set(nullptr, 0);
         codec_trace_set(nullptr, 0);
         cudaFree(trace_dev);
-        const char* names[WF_TR_SLOTS] = {"scatter start", "prev start", "chain start", "chain end", "rows start", "rows flag", "old start", "old end"};
+        const char* names[WF_TR_SLOTS] = {"scatter start", "prev start", "chain start", "chain end", "rows start", "rows flag", "old start", "old end", "R tail start", "R tail end"};
         for (int w0 = 0; w0 < 2; w0++) {  // two windows: while the importance stream still runs / after it finished
             const int pa = tr_sel ? (w0 == 0 ? 10 : 50) : (w0 == 0 ? 20 : 140), pb = tr_sel ? (w0 == 0 ? 45 : 90) : (w0 == 0 ? 80 : 220);
             double acc[WF_TR_SLOTS] = {0}, period = 0;
@@ -1083,6 +1182,21 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
             fprintf(stderr, "lic360 trace, %s-stream steps %d..%d: period %.1f us;", tr_sel ? "importance" : "code", pa, pb, period / cnt);
             for (int k = 1; k < WF_TR_SLOTS; k++) fprintf(stderr, " %s +%.1f;", names[k], acc[k] / cnt);
             fprintf(stderr, "\n");
+        }
+        if (const char* fn = getenv("LIC360_WF_TRACE_FILE")) {  // per-step dump: step, slab length, us relative to the step's slot 0, period
+            if (FILE* f = fopen(fn, "w")) {
+                fprintf(f, "step,len,prev_start,chain_start,chain_end,rows_start,rows_last,old_start,old_end,tail_start,tail_end,period,host_wait_us,host_decode_us,levels_wait_us\n");
+                for (int p = 0; p + 1 < tr_net.nsteps; p++) {
+                    const unsigned long long* r = &tr[(size_t)p * WF_TR_SLOTS];
+                    fprintf(f, "%d,%d", p, tr_net.steps[p].len);
+                    for (int k = 1; k < WF_TR_SLOTS; k++) fprintf(f, ",%.1f", (double)(long long)(r[k] - r[0]) * 1e-3);
+                    fprintf(f, ",%.1f", (double)(long long)(tr[(size_t)(p + 1) * WF_TR_SLOTS] - r[0]) * 1e-3);
+                    fprintf(f, ",%.1f,%.1f,%.1f\n", (size_t)p < tr_net.step_wait_us.size() ? tr_net.step_wait_us[p] : 0.f,
+                            (size_t)p < tr_net.step_decode_us.size() ? tr_net.step_decode_us[p] : 0.f,
+                            (size_t)p < tr_net.step_levels_us.size() ? tr_net.step_levels_us[p] : 0.f);
+                }
+                fclose(f);
+            }
         }
         if (!tr_sel) {
             fprintf(stderr, "lic360 trace, code-stream chain, CTA 0 thread 0, us per layer [weight staging issue | item: 25 loads, 100 FMA4, stores | prefetch issue + weights landed | cluster barrier]:");
@@ -1114,7 +1228,8 @@ int lic360_codec_last_timing(lic360_codec* c, double* out, int n) {
 }
 
 int lic360_codec_set_mode(lic360_codec* c, int mode) {
-    LIC360_CHECK_ARG(c && (mode == 0 || mode == 1), "mode must be 0 (pipelined graph replay) or 1 (serialized, per-kernel timing)");
+    LIC360_CHECK_ARG(c && (mode == 0 || mode == 1 || mode == 2),
+                     "mode must be 0 (pipelined graph replay per step), 1 (serialized, per-kernel timing) or 2 (low latency: persistent code-stream chain)");
     c->mode = mode;
     return LIC360_OK;
 }

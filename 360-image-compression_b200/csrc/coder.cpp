@@ -267,8 +267,21 @@ struct DecState {
 };
 
 template <bool kTagged>
-static int decode_packed_gmm_impl(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx) {
+static int decode_packed_gmm_impl(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx,
+                                  uint32_t sym_tag = 0) {
     DecState st{(uint32_t)c->low, (uint32_t)c->high, (uint32_t)c->code, &c->br};
+    // sym_tag != 0 (persistent decode): every symbol word is self-validating for the GPU threads that poll it -- the low 4 mantissa
+    // bits of the float (zero for 0..7 and for the fill value) carry the step's publication tag
+    auto put = [sym_tag](float* dst, float v) {
+        if (kTagged && sym_tag) {
+            uint32_t b;
+            memcpy(&b, &v, 4);
+            b |= sym_tag;
+            __atomic_store_n(reinterpret_cast<uint32_t*>(dst), b, __ATOMIC_RELAXED);
+        } else {
+            *dst = v;
+        }
+    };
     const float fill = c->fill;
     int rc = LIC360_OK;
     for (int i = 0; i < nrows; i++) {
@@ -291,7 +304,7 @@ static int decode_packed_gmm_impl(lic360_coder* c, const uint16_t* rows, int nro
         // the hardware prefetcher little to go on -- ask for the lines ahead
         __builtin_prefetch(r + 8 * 24);
         const uint32_t meta = r[7];
-        if (!((meta >> 8) & 1)) { out[i] = fill; continue; }  // coder.cpp:101-102
+        if (!((meta >> 8) & 1)) { put(out + i, fill); continue; }  // coder.cpp:101-102
         const uint64_t range = (uint64_t)st.high - st.low + 1;
         const uint64_t num = (((uint64_t)(st.code - st.low) + 1) << 16) - 1;
         uint64_t prod[9];
@@ -309,7 +322,7 @@ static int decode_packed_gmm_impl(lic360_coder* c, const uint16_t* rows, int nro
             rc = LIC360_ERR_CODER;
             break;
         }
-        out[i] = (float)s;
+        put(out + i, (float)s);
     }
     c->low = st.low; c->high = st.high; c->code = st.code;
     return rc;
@@ -319,8 +332,14 @@ int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, fl
     return decode_packed_gmm_impl<false>(c, rows, nrows, out, 0, nullptr, nullptr);
 }
 
-int coder_decode_packed_gmm_tagged(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx) {
-    return decode_packed_gmm_impl<true>(c, rows, nrows, out, tag, stalled, ctx);
+int coder_decode_packed_gmm_tagged(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx,
+                                   unsigned sym_tag) {
+    if (sym_tag) {
+        uint32_t fb;
+        memcpy(&fb, &c->fill, 4);
+        if ((fb & 15u) || sym_tag > 15u) { set_error("coder: symbol tags need a fill value with four zero low mantissa bits"); return LIC360_ERR_ARG; }
+    }
+    return decode_packed_gmm_impl<true>(c, rows, nrows, out, tag, stalled, ctx, sym_tag);
 }
 
 static inline uint32_t imp_bin(const uint16_t* r, int j) {  // j in 0..49

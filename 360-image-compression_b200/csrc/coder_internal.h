@@ -15,7 +15,9 @@ int coder_encode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows);
 int coder_decode_packed_gmm(lic360_coder* c, const uint16_t* rows, int nrows, float* out);
 // the decoder's per-step rows when they carry a publication tag (meta bits 4..7): row i is decoded as soon as its tag equals `tag`;
 // `stalled` is called every few thousand polls of a missing row and returns non-zero to give up (its value is returned)
-int coder_decode_packed_gmm_tagged(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx);
+// sym_tag != 0: the decoded symbol words carry that tag in their four low mantissa bits (polled by the persistent chain kernel)
+int coder_decode_packed_gmm_tagged(lic360_coder* c, const uint16_t* rows, int nrows, float* out, int tag, int (*stalled)(void*), void* ctx,
+                                   unsigned sym_tag = 0);
 int coder_encode_packed_imp(lic360_coder* c, const uint16_t* rows, int nrows);
 int coder_decode_packed_imp(lic360_coder* c, const uint16_t* rows, int nrows, float* out);
 const uint8_t* coder_bytes(lic360_coder* c, long* n);

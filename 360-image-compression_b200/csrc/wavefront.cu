@@ -179,12 +179,13 @@ constexpr int WF2_BAND_BYTES = WF2_STAGE * WF2_BAND * 4;
 constexpr int WF2_STAGE_BYTES = ((WF2_BAND_BYTES + WF2_STAGE * TAPS * 16 + 127) / 128) * 128;
 
 __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old2_kernel(const __grid_constant__ WfNetDev net,
-                                                                   const __grid_constant__ WfMaps maps, int dp, int l0, int parts2) {
+                                                                   const __grid_constant__ WfMaps maps, int dp, int l0, int parts2, int psum_x,
+                                                                   const int* __restrict__ scat_done) {
     extern __shared__ unsigned char wf_raw[];
     // grid = ((layer, net), chunk, (diagonal, part)), x fastest: the heaviest output groups of every layer start first
     const int bx = blockIdx.z, bz = blockIdx.x;
     const int l = l0 + bz / net.nsets, n = bz % net.nsets, kc = blockIdx.y;
-    const int psum = *net.ctr + dp;
+    const int psum = psum_x >= 0 ? psum_x : *net.ctr + dp;  // explicit step: persistent decode (the host paces the steps)
     if (kc >= net.L[l].cpg4 || psum >= net.nsteps) return;
     const int la = max(0, psum - net.G + 1), lb = min(psum, net.H + net.W - 2);
     const int d = la + bx / parts2;
@@ -194,6 +195,21 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old2_kernel(const __grid
     if (hb > hmax) return;                             // CTA-uniform
     const int tc = psum - d;
     if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(net.G, psum - dp, WF_TR_OLD0);
+    if (scat_done && l == 0) {
+        // persistent decode: this launch was enqueued right behind the host's go for step psum - 1; layer 0 reads the symbols of steps
+        // <= psum - 2, which the chain kernel scatters at the top of step psum - 1 -- normally long done, but not ordered by any stream
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            unsigned long long t0 = 0, t1 = 0;
+            for (unsigned spins = 1; reinterpret_cast<const volatile int*>(scat_done)[n] < psum - 1; spins++)
+                if ((spins & 0xFFF) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t0 == 0) t0 = t1;
+                    else if (t1 - t0 > 5000000000ull) break;
+                }
+            __threadfence();
+        }
+        __syncthreads();
+    }
     const WfLayerDev& L = net.L[l];
     const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
     unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
@@ -589,8 +605,10 @@ struct WfPre { float4 pr, rr; float bs[4], sl[4], rs[4]; };  // P and R: added w
 
 __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const WfLayerDev& L, int n, int par, int d, int h, int tc,
                                                    WfPre& p) {
-    p.pr = __ldg(L.pbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
-    p.rr = __ldg(L.rbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
+    // L2 loads (not the read-only path): in the persistent decode these sums are produced while this kernel is running -- P by the
+    // concurrently running old-term kernel, R by this cluster's own tail of the previous step
+    p.pr = __ldcg(L.pbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
+    p.rr = __ldcg(L.rbuf[par] + ((size_t)n * net.D + d) * net.HS + h);
     const size_t fc = wf_fc_index(net.Dp, net.Hp, net.G, L.cout_g, n, d, tc, h);
     const int o0 = tc * L.cout_g;
 #pragma unroll
@@ -606,6 +624,8 @@ __device__ __forceinline__ void wf_chain4_prefetch(const WfNetDev& net, const Wf
 // they read the symbols the host decoded a moment ago, so they cannot be computed a step ahead like the other layers'.
 // 25 activations and 25 weight vectors, all in flight together; groups outside [0, G) read the zero padding of the group
 // axis and carry zero weights.  Non-inlined: runs once per step, outside the layer loop.
+// COHERENT: the symbols were scattered by THIS kernel (persistent decode) -> L2 loads instead of the read-only path
+template <bool COHERENT = false>
 __device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d, int h, int tc, int kc = 0) {
     const WfLayerDev& L = net.L[0];
     const int GP = net.G + 2 * WF_GPAD;
@@ -618,7 +638,7 @@ __device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d,
     for (int kh = 0; kh < 5; kh++)
 #pragma unroll
         for (int kw = 0; kw < 5; kw++) {
-            xv[kh * 5 + kw] = __ldg(xr + (kh + kw) * srow + kh);
+            xv[kh * 5 + kw] = COHERENT ? __ldcg(xr + (kh + kw) * srow + kh) : __ldg(xr + (kh + kw) * srow + kh);
             wv[kh * 5 + kw] = __ldg(w + kh * 5 + kw);
         }
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -629,14 +649,56 @@ __device__ __noinline__ float4 wf_r_layer0_c1(const WfNetDev& net, int n, int d,
     return make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0 (one canonical block)
 }
 
+// Previous-wavefront terms R of step p + 1 (layers 1..11) are evaluated by the chain kernel of step p behind its CDF rows (wf_chain4_rtail).
+// This CTA takes the same chunk of the NEXT slab it will own in the next step's chain; the R weight rows of that chunk's output groups, for
+// as many layers as fit (all 11 unless the chunk spans many groups), are copied to shared memory while the CTA waits for the other
+// clusters in wf_chain4_rows -- the tail then runs from shared-memory weights like the chain itself.
+struct WfTailPlan { int i0, nloc, tc_lo, nrows, lpg; };
+
+__device__ __forceinline__ WfTailPlan wf_tail_plan(const WfNetDev& net, int rank, int nc, int psum1, int smem_rows) {
+    WfTailPlan t = {0, 0, 0, 0, 1};
+    if (psum1 >= net.nsteps) return t;
+    const StepDesc s1 = net.steps[psum1];
+    const int per = (s1.len + nc - 1) / nc;
+    t.i0 = min(s1.len, rank * per);
+    const int i1 = min(s1.len, t.i0 + per);
+    t.nloc = i1 - t.i0;
+    if (t.nloc > 0) {  // plan order is diagonal-major: the chunk's output groups are a contiguous range
+        const int HW = net.H * net.W, ka = s1.start + t.i0, kb = s1.start + i1 - 1;
+        const int tc_hi = psum1 - __ldg(net.idx + ka) - __ldg(net.idx + ka + HW);
+        t.tc_lo = psum1 - __ldg(net.idx + kb) - __ldg(net.idx + kb + HW);
+        t.nrows = tc_hi - t.tc_lo + 1;
+        t.lpg = max(1, min(WF_LAYERS - 1, smem_rows / t.nrows));
+    }
+    return t;
+}
+
+// cp.async of the R rows [tc_lo, tc_lo + nrows) of layers l0 .. l0 + nl - 1 into the dynamic shared memory, issued by threads t0, t0 + 1, ..
+__device__ __forceinline__ void wf_tail_stage(const WfNetDev& net, int n, const WfTailPlan& t, int l0, int nl, int tid, int t0, int nthr) {
+    extern __shared__ float4 wf_wsm[];
+    if (tid >= t0) {
+        const int per_layer = t.nrows * WF_ROW_F4;
+        for (int lr = 0; lr < nl; lr++) {
+            const WfLayerDev& L = net.L[l0 + lr];
+            const float4* src = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + t.tc_lo) * WF_ROW_F4;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(wf_wsm + (size_t)lr * per_layer);
+            for (int e = tid - t0; e < per_layer; e += nthr) cp_async16(dst + 16u * e, src + e);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+}
+
 // CDF rows of the step (TileExtract + EntropyGmmTable fused) at the end of the chain kernel: a row needs the outputs of all
 // three nets, so the clusters meet at a monotone global counter first (every CTA of the grid is resident or becomes
 // resident without needing anything from the waiting ones: no deadlock).  A separate, non-inlined function: its register
 // needs (erff, the 9-bin row) stay out of the chain's layer loop.
-__device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& rows, int psum, int start, int len, int tid, int nt) {
+__device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& rows, int psum, int start, int len, int tid, int nt,
+                                            int n, const WfTailPlan& tail) {
     __shared__ int s_abort;
     __threadfence();
     __syncthreads();
+    // the layer loop is done with the weight buffers: warps 1.. fill them with the R rows of the tail while thread 0 meets the other clusters
+    if (rows.rtail && tail.nloc > 0) wf_tail_stage(net, n, tail, 1, min(tail.lpg, WF_LAYERS - 1), tid, 32, nt - 32);
     if (tid == 0) {
         atomicAdd(rows.sync, 1);
         const int target = (psum + 1) * (int)gridDim.x;
@@ -698,7 +760,7 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
         }
         if (live && j == 0) {
             fixup_row(o, 8, true);
-            const int lvl = (int)(rows.levels[(th >> 1) * (W >> 1) + (tw >> 1)] + 1e-5f);
+            const int lvl = (int)(__ldcg(rows.levels + (th >> 1) * (W >> 1) + (tw >> 1)) + 1e-5f);  // written by the other stream's kernels
             pack_gmm_row(o, 0, (4 * tc + 2 * (th & 1) + (tw & 1)) < 4 * lvl ? 1 : 0, rows.rows + (size_t)li * 8, rows.tagged ? psum % 15 + 1 : 0);
         }
     }
@@ -722,54 +784,167 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
 // them (wf_prev_kernel) was observed to start only when the concurrently running old-term kernel drained (+30 us on the step).
 // One item = (layer, slab position of step p + 1); arithmetic = one canonical block of 4 channels, taps in (kh, kw, c) order,
 // every tap read unconditionally from the group-padded frame (out-of-range groups are zeros times zero weights).
-__device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int rank, int nc, int psum1, int tid, int nt) {
-    if (psum1 >= net.nsteps) return;
-    if (tid == 0) WF_TRACE_MIN(net.G, psum1 - 1, WF_TR_PREV);
+__device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int psum1, int tid, int nt, const WfTailPlan& tail) {
+    extern __shared__ float4 wf_wsm[];
+    if (psum1 >= net.nsteps || tail.nloc == 0) return;  // uniform per CTA
+    if (tid == 0) WF_TRACE_MIN(net.G, psum1 - 1, WF_TR_TAIL0);
     const StepDesc s1 = net.steps[psum1];
     const int HW = net.H * net.W, GP = net.G + 2 * WF_GPAD;
     const size_t srow = (size_t)(GP - 1) * net.Hp;
-    const int items = (WF_LAYERS - 1) * s1.len;
-    for (int it = rank * nt + tid; it < items; it += nc * nt) {
-        const int l = 1 + it / s1.len, li = it % s1.len;
-        const WfLayerDev& L = net.L[l];
-        const int k = s1.start + li;
-        const int h = __ldg(net.idx + k), d = h + __ldg(net.idx + k + HW), tc = psum1 - d;
-        // tap (kh, kw), s = kh + kw, selects group tc + 3 - s: cell = xr + s * srow + kh, float4 units
-        const float4* xr = reinterpret_cast<const float4*>(L.xc) + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
-        const float4* wr = reinterpret_cast<const float4*>(L.wq) + ((size_t)n * L.nchunk + tc) * WF_ROW_F4;
-        float4 xv[TAPS];
+    for (int l0 = 1; l0 < WF_LAYERS; l0 += tail.lpg) {
+        const int nl = min(tail.lpg, WF_LAYERS - l0);
+        if (l0 > 1) {  // (the first group was staged in wf_chain4_rows)
+            __syncthreads();
+            wf_tail_stage(net, n, tail, l0, nl, tid, 0, nt);
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        for (int it = tid; it < nl * tail.nloc; it += nt) {
+            const int lr = it / tail.nloc, il = it - lr * tail.nloc;
+            const WfLayerDev& L = net.L[l0 + lr];
+            const int k = s1.start + tail.i0 + il;
+            const int h = __ldg(net.idx + k), d = h + __ldg(net.idx + k + HW), tc = psum1 - d;
+            // tap (kh, kw), s = kh + kw, selects group tc + 3 - s: cell = xr + s * srow + kh, float4 units
+            const float4* xr = reinterpret_cast<const float4*>(L.xc) + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
+            const float4* wr = wf_wsm + ((size_t)lr * tail.nrows + (tc - tail.tc_lo)) * WF_ROW_F4;
+            float4 xv[TAPS];
 #pragma unroll
-        for (int kh = 0; kh < 5; kh++)
+            for (int kh = 0; kh < 5; kh++)
 #pragma unroll
-            for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = WF_TAP_LOAD(xr + (kh + kw) * srow + kh);  // this cluster's stores, behind its barriers
-        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = WF_TAP_LOAD(xr + (kh + kw) * srow + kh);  // this cluster's stores, behind its barriers
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int kh = 0; kh < 5; kh++)
+            for (int kh = 0; kh < 5; kh++)
 #pragma unroll
-            for (int kw = 0; kw < 5; kw++) {
-                const float4 x4 = xv[kh * 5 + kw];
-                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                for (int kw = 0; kw < 5; kw++) {
+                    const float4 x4 = xv[kh * 5 + kw];
+                    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const float4 w4 = __ldg(wr + (kh * 5 + kw) * 4 + c);
-                    fma4(u, xs[c], w4);
+                    for (int c = 0; c < 4; c++) {
+                        const float4 w4 = wr[(kh * 5 + kw) * 4 + c];
+                        fma4(u, xs[c], w4);
+                    }
+                }
+            L.rbuf[psum1 & 1][((size_t)n * net.D + d) * net.HS + h] = make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0
+        }
+    }
+    __syncthreads();  // the next step's (or launch's) layer loop stages into these buffers again
+    if (tid == 0) WF_TRACE_MAX(net.G, psum1 - 1, WF_TR_TAIL1);
+}
+
+// Persistent decode (WfPersist): what the chain kernel does between two steps instead of being re-launched.
+// wf_chain4_wait_old: the old-term sums of step p are complete (the old-term kernel of step p was enqueued a whole step ago; normally
+// this returns at once).  Runs BEFORE the go so that P, R, bias and slope of the step's first layer are in registers when it comes.
+__device__ __noinline__ void wf_chain4_wait_old(const WfPersist& ps, int p, int tid) {
+    if (tid == 0) {
+        unsigned long long t0 = 0, t1 = 0;
+        for (unsigned spins = 1; *reinterpret_cast<const volatile int*>(ps.old_done) < p + 1; spins++) {
+            if ((spins & 0xFFF) == 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                else if (t1 - t0 > 5000000000ull) break;  // the step then runs on incomplete sums and the decode fails on the host side
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// wf_chain4_step_begin, top of step p:
+//   warps 1..: TileInput (tile_input_cuda.cu:27-43) of the symbols of step p - 1 into this cluster's copy of the input frame, both
+//     layouts.  The host publishes every symbol as it decodes it, as a self-validating word (tag of step p - 1 in the four low mantissa
+//     bits), so each thread polls ITS word in mapped host memory and scatters it at once: when the host has decoded the last symbol the
+//     frame is complete but for that symbol's PCIe read.
+//   thread 0: waits for the host's go -- CTA 0 polls the mapped host flag and republishes the decision in device memory so that every
+//     CTA of the grid takes the SAME decision at the same step boundary (run step p, or abort instead of running it).
+//   then a cluster barrier publishes the scatter to the whole cluster, and CTA 0 of the cluster tells the old-term kernels.
+// Every spin has a bail-out so that a lost host or a lost kernel ends in an error, not a hang.  Returns false when the decode is to be
+// abandoned.
+__device__ __noinline__ bool wf_chain4_step_begin(const WfNetDev& net, const WfPersist& ps, int p, int n, int rank, int nc, int tid, int nt) {
+    __shared__ int s_go;  // 0 = undecided, 1 = run, -1 = abort
+    if (tid == 0) s_go = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int decision = 0;
+        unsigned long long t0 = 0, t1 = 0;
+        if (blockIdx.x == 0) {
+            for (unsigned spins = 1; decision == 0; spins++) {
+                const int v = *reinterpret_cast<const volatile int*>(ps.go_host);
+                if (v == WF_GO_ABORT) decision = -1;
+                else if (v >= p) decision = 1;
+                else if ((spins & 0xFF) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t0 == 0) t0 = t1;
+                    else if (t1 - t0 > 20000000000ull) decision = -1;  // 20 s without a host: give up
                 }
             }
-        L.rbuf[psum1 & 1][((size_t)n * net.D + d) * net.HS + h] = make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0
+            WF_TRACE_MIN(net.G, p, WF_TR_SCATTER);  // debug timeline: the go of step p has reached the device
+            *reinterpret_cast<volatile int*>(ps.go_dev) = decision > 0 ? p : -(p + 2);
+            if (decision > 0) *reinterpret_cast<volatile int*>(ps.ctr) = p;
+        } else {
+            for (unsigned spins = 1; decision == 0; spins++) {
+                const int v = *reinterpret_cast<const volatile int*>(ps.go_dev);
+                if (v >= p) decision = 1;
+                else if (v < -1 && -(v + 2) <= p) decision = -1;  // -1 is the initial value: nothing decided yet
+                else if ((spins & 0xFFF) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t0 == 0) t0 = t1;
+                    else if (t1 - t0 > 30000000000ull) decision = -1;
+                }
+            }
+        }
+        *reinterpret_cast<volatile int*>(&s_go) = decision;
+    } else if (tid >= 32 && p > 0) {
+        const StepDesc d = net.steps[p - 1];
+        const int HW = net.H * net.W, nw = nt - 32;
+        const unsigned tag = (unsigned)((p - 1) % 15 + 1);
+        float* fp0 = const_cast<float*>(net.L[0].xp);
+        float* fc0 = const_cast<float*>(net.L[0].xc);
+        const unsigned* words = reinterpret_cast<const unsigned*>(ps.syms);
+        bool dead = false;
+        for (int l = rank * nw + tid - 32; l < d.len && !dead; l += nc * nw) {
+            const int th = __ldg(net.idx + d.start + l), tw = __ldg(net.idx + d.start + l + HW);
+            const int tc = d.psum - th - tw;
+            unsigned bits;
+            for (;;) {
+                bits = __ldcv(words + l);  // mapped host memory: never from a cached line
+                if ((bits & 15u) == tag) break;
+                if (*reinterpret_cast<volatile int*>(&s_go) < 0) { dead = true; break; }  // the go can only come after the symbols
+            }
+            if (dead) break;
+            const float v = fmaf(ps.scale, __uint_as_float(bits & ~15u), ps.bias);
+            fp0[wf_fp_index(net.D, net.HS, net.G, n, tc, th + tw, th)] = v;
+            fc0[wf_fc_index(net.Dp, net.Hp, net.G, 1, n, th + tw, tc, th)] = v;
+        }
     }
+    __syncthreads();
+    if (s_go < 0) return false;
+    if (nc > 1) cg::this_cluster().sync();
+    else __syncthreads();
+    if (rank == 0 && tid == 0) {  // this net's frame now holds the symbols of every step < p
+        if (n == 0) WF_TRACE_MIN(net.G, p, WF_TR_PREV);  // debug timeline: scatter + cluster barrier done
+        __threadfence();
+        reinterpret_cast<volatile int*>(ps.scat_done)[n] = p;
+    }
+    return true;
 }
 
 __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant__ WfNetDev net, int nc, int rows_cap,
-                                                         const __grid_constant__ WfRows rows, int r0_inline) {
+                                                         const __grid_constant__ WfRows rows, int r0_inline,
+                                                         const __grid_constant__ WfPersist persist, int smem_rows) {
     extern __shared__ float4 wf_wsm[];  // [2][rows_cap][WF_ROW_F4]
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n = blockIdx.x / nc, rank = blockIdx.x % nc;
     // programmatic dependent launch: the old-term kernel of the next step may start as soon as every CTA of this kernel is
     // resident (it does not read anything this kernel writes); without that launch attribute this is a no-op
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    const StepDesc sd = net.steps[*net.ctr];
-    const int HW = net.H * net.W, par = sd.psum & 1;
-    if (threadIdx.x == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_CHAIN0);
+    const int HW = net.H * net.W;
+    // one step per launch (graph replay: the step is read from the device counter) or all of them (persistent decode)
+    const int step_first = persist.enabled ? 0 : *net.ctr, step_last = persist.enabled ? net.nsteps : step_first + 1;
+  for (int step = step_first; step < step_last; step++) {
+    const StepDesc sd = net.steps[step];
+    const int par = sd.psum & 1;
+    if (!persist.enabled && threadIdx.x == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_CHAIN0);
     const int per = (sd.len + nc - 1) / nc;
     const int i0 = min(sd.len, rank * per), i1 = min(sd.len, i0 + per), nloc = i1 - i0;
     // plan order is diagonal-major, so the output groups of this CTA's items are the contiguous range [tc_lo, tc_hi]
@@ -790,10 +965,14 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
         tc0 = sd.psum - d0;
     }
     WfPre pre;
-    if (has0) {
-        wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
-        if (r0_inline) pre.rr = wf_r_layer0_c1(net, n, d0, h0, tc0);  // no launch computed layer 0's R for this step
+    if (persist.enabled) wf_chain4_wait_old(persist, step, tid);
+    if (has0) wf_chain4_prefetch(net, net.L[0], n, par, d0, h0, tc0, pre);
+    if (persist.enabled) {  // everything above is in flight or done when the host's go arrives
+        if (!wf_chain4_step_begin(net, persist, step, n, rank, nc, tid, nt)) return;
+        if (threadIdx.x == 0) WF_TRACE_MIN(net.G, sd.psum, WF_TR_CHAIN0);
     }
+    // no launch computed layer 0's R for this step
+    if (has0 && r0_inline) pre.rr = persist.enabled ? wf_r_layer0_c1<true>(net, n, d0, h0, tc0) : wf_r_layer0_c1<false>(net, n, d0, h0, tc0);
     // debug timeline (LIC360_WF_TRACE=1): ns spent by thread 0 of CTA 0 in the phases of every layer, accumulated behind the step slots
     const bool phase_trace = g_wf_trace && g_wf_trace_sel == 0 && blockIdx.x == 0 && tid == 0;
     unsigned long long tph = 0;
@@ -826,7 +1005,7 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
                 d = h + __ldg(net.idx + k + HW);
                 tc = sd.psum - d;
                 wf_chain4_prefetch(net, L, n, par, d, h, tc, p);
-                if (l == 0 && r0_inline) p.rr = wf_r_layer0_c1(net, n, d, h, tc);
+                if (l == 0 && r0_inline) p.rr = persist.enabled ? wf_r_layer0_c1<true>(net, n, d, h, tc) : wf_r_layer0_c1<false>(net, n, d, h, tc);
             }
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             if (L.has_q) {
@@ -902,8 +1081,16 @@ __global__ void __launch_bounds__(384, 1) wf_chain4_kernel(const __grid_constant
         phase(l, 3);
     }
     if (threadIdx.x == 0) WF_TRACE_MAX(net.G, sd.psum, WF_TR_CHAIN1);
-    if (rows.enabled) wf_chain4_rows(net, rows, sd.psum, sd.start, sd.len, tid, nt);
-    if (rows.enabled && rows.rtail) wf_chain4_rtail(net, n, rank, nc, sd.psum + 1, tid, nt);
+    if (rows.enabled) {
+        const WfTailPlan tail = wf_tail_plan(net, rank, nc, sd.psum + 1, smem_rows);
+        wf_chain4_rows(net, rows, sd.psum, sd.start, sd.len, tid, nt, n, tail);
+        if (rows.rtail) wf_chain4_rtail(net, n, sd.psum + 1, tid, nt, tail);
+    }
+    if (persist.enabled) {  // the next step prefetches the R sums the tail just stored (other CTAs of the cluster) before its go
+        if (nc > 1) cg::this_cluster().sync();
+        else __syncthreads();
+    }
+  }  // step
 }
 
 // Chain for single-group nets (the importance stream: G = 1, 144 channels).  A step is ONE anti-diagonal (<= min(H,W)
@@ -1371,7 +1558,13 @@ cudaError_t wf_clear(const WfEngine& e, cudaStream_t s) {
     return cudaMemsetAsync(e.pbuf, 0, e.pbuf_f4 * sizeof(float4), s);
 }
 
-cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic) {
+// behind an old-term launch in the same stream: the sums of steps < value are complete and visible
+__global__ void wf_old_done_kernel(int* done, int value) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(done) = value;
+}
+
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic, int psum, int* done, const int* scat_done) {
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1391,9 +1584,15 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
         cfg.gridDim = dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * (e.old2 ? e.parts2 : n.parts));
         cfg.numAttrs = programmatic && k == 0 ? 1 : 0;
         g_launches++;
-        const cudaError_t err = e.old2 ? cudaLaunchKernelEx(&cfg, wf_old2_kernel, n, e.maps2, dp, l0, e.parts2)
+        if (psum >= 0 && !e.old2) return cudaErrorInvalidValue;  // explicit steps: many-group engines only
+        const cudaError_t err = e.old2 ? cudaLaunchKernelEx(&cfg, wf_old2_kernel, n, e.maps2, dp, l0, e.parts2, psum, scat_done)
                                        : cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
         if (err != cudaSuccess) return err;
+    }
+    if (done) {
+        wf_old_done_kernel<<<1, 1, 0, s>>>(done, psum + 1);
+        g_launches++;
+        return cudaGetLastError();
     }
     return cudaSuccess;
 }
@@ -1409,10 +1608,17 @@ cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows) {
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows, const WfPersist* persist) {
     WfRows r;
     memset(&r, 0, sizeof(r));
     if (rows && (e.chain4 || e.chain1)) r = *rows;
+    WfPersist ps;
+    memset(&ps, 0, sizeof(ps));
+    if (persist) {
+        if (!e.chain4 || !r.enabled || !r.rtail || !e.r0_inline) return cudaErrorInvalidValue;  // the persistent loop assumes the fully fused step
+        ps = *persist;
+        ps.enabled = 1;
+    }
     const WfNetDev& n = e.dev;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1426,7 +1632,8 @@ cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* row
     cfg.attrs = attr;
     cfg.numAttrs = e.cluster > 1 ? 1 : 0;
     g_launches++;
-    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r, (int)(e.r0_inline && r.enabled));
+    if (e.chain4) return cudaLaunchKernelEx(&cfg, wf_chain4_kernel, n, e.cluster, n.G, r, (int)(e.r0_inline && r.enabled), ps,
+                                            (int)(e.chain_smem / (WF_ROW_F4 * sizeof(float4))));
     if (e.chain1) return cudaLaunchKernelEx(&cfg, wf_chain1_kernel, n, e.cluster, e.c1_kpc, e.c1_lenp, e.c1_cmax, r, (int)(e.r0_inline && r.enabled), (int)e.c1_dsm);
     return cudaLaunchKernelEx(&cfg, wf_chain_kernel<384>, n, e.cluster);
 }

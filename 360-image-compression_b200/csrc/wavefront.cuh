@@ -54,6 +54,21 @@ struct WfRows {
     int tagged;           // rows carry the publication tag step % 15 + 1 and are NOT followed by a system fence + flag: the host validates row by row
 };
 
+// Low-latency ("persistent") decode of the many-group stream: ONE launch of the chain kernel walks all wavefront steps; between steps it
+// waits for the host instead of being re-launched (no graph launch, no scatter kernel, no kernel prologue on the critical path).
+struct WfPersist {
+    const float* syms;   // mapped pinned: the symbols the host decoded for the previous step
+    const int* go_host;  // mapped pinned, host -> device: step p may run once *go_host >= p; WF_GO_ABORT: stop at the next step boundary
+    int* go_dev;         // device: CTA 0 republishes the host's decision here (p = run step p, -(p + 2) = abort instead of running p)
+    const int* old_done; // device: old-term sums of steps < *old_done are complete (set by wf_old_done_kernel behind every old-term launch)
+    int* ctr;            // device step counter kept up to date for the kernels that follow the decode (final scatter)
+    int* scat_done;      // device, one per net: the symbols of steps < scat_done[n] are in net n's input frame (the old-term kernel of
+                         // step q, enqueued by the host right behind go(q - 1), reads wavefronts <= q - 2 of that frame: it waits for q - 1)
+    float bias, scale;   // TileInput: value = scale * symbol + bias
+    int enabled;
+};
+constexpr int WF_GO_ABORT = -2;
+
 struct WfMaps { CUtensorMap tm[WF_LAYERS]; };  // FP input frame of every layer, box {40 h, 9 d, 4 c}
 
 struct WfEngine {
@@ -89,11 +104,15 @@ const void* wf_old_kernel_ptr();
 const void* wf_old2_kernel_ptr();  // to give the old-term kernel node its own (lowest) priority in the step graph
 cudaError_t wf_clear(const WfEngine& e, cudaStream_t s);                    // zero every frame (start of a decode)
 // P of step *ctr + dp, all layers.  programmatic: launch as a programmatic dependent of the previous kernel in the stream
-cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic = false);
+// psum >= 0: explicit step (persistent decode: the host knows it), else *ctr + dp.  done != nullptr: a one-thread kernel behind the launch
+// publishes *done = psum + 1 (stream order: the old-term sums of that step are complete)
+cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool programmatic = false, int psum = -1, int* done = nullptr,
+                          const int* scat_done = nullptr);
 // R of step *ctr + dp for layers [l0, l1): layer 0 at dp = 0 right after the scatter (it reads the symbols just decoded),
 // layers 1..11 at dp = 1 right after the chain (underneath the host decoder)
 cudaError_t wf_launch_prev(const WfEngine& e, int dp, int l0, int l1, cudaStream_t s);
-cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows = nullptr);  // the 12-layer chain of step *ctr
+// the 12-layer chain of step *ctr; persist != nullptr (chain4 engines only): all steps in one launch, paced by the host through persist->go_host
+cudaError_t wf_launch_chain(const WfEngine& e, cudaStream_t s, const WfRows* rows = nullptr, const WfPersist* persist = nullptr);
 
 // first channel of group g at (d, h); cpg = channels per group of that frame.  The group axis carries WF_GPAD zero
 // groups on each side: a tap of the R / Q terms may select group -5 .. G+3, which then reads zeros instead of needing a test.
@@ -103,7 +122,7 @@ __host__ __device__ inline size_t wf_fc_index(int Dp, int Hp, int G, int cpg, in
 }
 // Debug timeline (LIC360_WF_TRACE=1): per step 8 slots of %globaltimer stamps.  Each translation unit has its own copy of
 // the device pointer (no relocatable device code); wf_trace_set() / codec_trace_set() point both at the same buffer.
-enum { WF_TR_SCATTER = 0, WF_TR_PREV, WF_TR_CHAIN0, WF_TR_CHAIN1, WF_TR_ROWS0, WF_TR_ROWS1, WF_TR_OLD0, WF_TR_OLD1, WF_TR_SLOTS };
+enum { WF_TR_SCATTER = 0, WF_TR_PREV, WF_TR_CHAIN0, WF_TR_CHAIN1, WF_TR_ROWS0, WF_TR_ROWS1, WF_TR_OLD0, WF_TR_OLD1, WF_TR_TAIL0, WF_TR_TAIL1, WF_TR_SLOTS };
 void wf_trace_set(unsigned long long* buf, int sel);  // sel: 0 = trace the multi-group (code) stream, 1 = the single-group (importance) stream
 #define WF_TRACE_DECL static __device__ unsigned long long* g_wf_trace = nullptr; static __device__ int g_wf_trace_sel = 0;
 #define WF_TRACE_MIN(G, step, slot)                                                                       \

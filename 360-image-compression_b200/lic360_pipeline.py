@@ -65,7 +65,9 @@ class FusedCodec(object):
     """The product path: one image per codec on its own CUDA stream, the whole encode / decode loop in native code
     (csrc/codec.cu): one graph replay + one host coder call per wavefront step, no Python in the loop."""
 
-    def __init__(self, params, H=64, W=128, gid=0):
+    def __init__(self, params, H=64, W=128, gid=0, mode=None):
+        """mode: None / 0 = graph replay per wavefront step (several images in flight per GPU), 2 = low latency (one persistent
+        chain kernel per decode; one image at a time), 1 = serialized per-kernel timing (profiling)."""
         self.H, self.W, self.gid = H, W, gid
         self.dev = torch.device('cuda', gid)
         h = LIB.lic360_codec_create(gid, H, W)
@@ -89,6 +91,9 @@ class FusedCodec(object):
                     raise RuntimeError("FusedCodec: %s.%s.relu is missing" % (key, lk))
                 check(LIB.lic360_codec_set_layer(self._h, sid, layer, w.data_ptr(), b.data_ptr(),
                                                  None if slope is None else slope.data_ptr()))
+
+        if mode:
+            self.set_mode(mode)
 
     def _param(self, t, shape, name):
         """float32, contiguous, on the codec's device, of the reference's shape -- anything else would be read as garbage
@@ -141,7 +146,8 @@ class FusedCodec(object):
         return code, mask
 
     def set_mode(self, mode):
-        """0: pipelined graph replay per step (default); 1: serialized launches with per-kernel CUDA-event timing."""
+        """0: pipelined graph replay per step (default); 1: serialized launches with per-kernel CUDA-event timing; 2: low latency
+        (one persistent code-stream chain kernel per decode, include/lic360_b200.h)."""
         check(LIB.lic360_codec_set_mode(self._h, int(mode)))
 
     def kernel_times(self, stream_id=0):

@@ -229,7 +229,11 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
  * [3] importance stream part of a decode, [4] CUDA-event time of all decode graph replays, [5] of the importance stream ones */
 int lic360_codec_last_timing(lic360_codec* c, double* out, int n);
 /* mode 0 (default): pipelined graph replay per wavefront step.  mode 1: the same kernels launched one by one on the codec
- * stream with CUDA events between them (the decode is serialized and slower; used by bench.py for the roofline block). */
+ * stream with CUDA events between them (the decode is serialized and slower; used by bench.py for the roofline block).
+ * mode 2 (low latency, opt-in): the code stream's chain kernel is launched ONCE per decode and walks all wavefront steps; between
+ * steps it polls the symbols the host publishes in mapped memory (every symbol word carries a publication tag) instead of being
+ * re-launched, so no graph launch, scatter kernel or kernel prologue sits between the host's last decoded symbol and the next
+ * step.  Same bitstreams, same results.  Its three 8-CTA clusters stay resident for the whole decode (24 SMs per decode in flight). */
 int lic360_codec_set_mode(lic360_codec* c, int mode);
 /* after a mode-1 decode: total milliseconds of the last decode spent in [0] the old-term kernel, [1] the previous-wavefront
  * kernel, [2] the 12-layer chain kernel, [3] scatter + CDF-row kernels, and [4] the number of steps, for one stream */

@@ -226,3 +226,56 @@ def test_fused_codec_stress_many_images_in_flight():
             x.join()
         del codecs
     assert not errors, errors
+
+
+@pytest.mark.parametrize("H,W,seed", [(8, 16, 51), (64, 128, 52), (96, 160, 53)])
+def test_fused_codec_low_latency_mode(H, W, seed):
+    """lic360_codec_set_mode(2): ONE launch of the code-stream chain kernel walks all wavefront steps (it polls the symbols the host
+    publishes, word by word, instead of being re-launched).  Same bytes in, same symbols out as the graph-replay decode; a truncated
+    stream ends in a coder error (or garbage), never in a hang; the codec object can switch back."""
+    import lic360_pipeline as pl
+    q, mask, lv = synthetic_latent(seed, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=seed)
+    fused = pl.FusedCodec(params, H=H, W=W, mode=2)
+    bi, bc = fused.encode(t(q, DEV), t(mask, DEV), t(lv, DEV))
+    for _ in range(2):
+        code, mup = fused.decode(bi, bc)
+        assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
+    try:
+        fused.decode(bi, bc[: len(bc) // 2])
+    except RuntimeError as e:
+        assert "coder" in str(e)
+    code, mup = fused.decode(bi, bc)  # the aborted decode left nothing behind
+    assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
+    fused.set_mode(0)
+    code0, mup0 = fused.decode(bi, bc)
+    assert np.array_equal(n(code0), n(code)) and np.array_equal(n(mup0), n(mup))
+
+
+def test_fused_codec_low_latency_mode_two_decodes_at_once():
+    """Two persistent decodes on one GPU (2 x 3 resident clusters) from two host threads: both finish, both exact."""
+    import threading
+    import lic360_pipeline as pl
+    H, W = 64, 128
+    params = pl.make_codec_params(DEV, seed=61)
+    codecs = [pl.FusedCodec(params, H=H, W=W, mode=2) for _ in range(2)]
+    lat = [synthetic_latent(600 + k, H=H, W=W) for k in range(2)]
+    errors = []
+
+    def worker(k):
+        try:
+            q, mask, lv = lat[k]
+            bi, bc = codecs[k].encode(t(q, DEV), t(mask, DEV), t(lv, DEV))
+            for _ in range(3):
+                code, mup = codecs[k].decode(bi, bc)
+                if not (np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)):
+                    errors.append((k, "mismatch"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors
