@@ -151,6 +151,63 @@ __device__ __forceinline__ void dc_stage_fma2(const float* band, const float4* w
     }
 }
 
+// Four adjacent positions of one diagonal per lane: 16 lanes cover 64 positions, and the other half-warp works on the NEXT diagonal
+// of the same band (its band rows are one further down, its weight vectors belong to the next lower output group).  bw points at the
+// 16-byte aligned cell of the lane's FIRST position for tap (0, 0); position i reads band cell [row][kh + i], so a row serves the four
+// positions with the cells kh_min .. kh_max + 3: at most two aligned float4 (16 loads per channel for 400 FMAs; the two-position form
+// needs 19 float2 for 200).  A weight vector is one LDS.128 with ONE ADDRESS PER HALF-WARP -- the cost of a broadcast, 2 wavefronts
+// (tools/lds_probe.cu) -- and feeds 16 FMAs instead of 8.  Per-accumulator FMA order = the canonical (kh, kw) order of dc_taps_fma.
+template <int BW, int NS>
+__device__ __forceinline__ void dc_taps_fma4(const float* bw, const float4* wrow, float4 (&u)[4]) {
+    float cell[9][8];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        if (r >= NS) continue;
+        const int khmin = r > 4 ? r - 4 : 0, khmax = r < 4 ? r : 4;
+#pragma unroll
+        for (int m = 0; m < 8; m += 4) {
+            if (m + 3 < khmin || m > khmax + 3) continue;
+            const float4 v = *reinterpret_cast<const float4*>(bw + r * BW + m);
+            cell[r][m] = v.x;
+            cell[r][m + 1] = v.y;
+            cell[r][m + 2] = v.z;
+            cell[r][m + 3] = v.w;
+        }
+    }
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++) {
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            if (kh + kw >= NS) continue;
+            const float4 w4 = wrow[kh * 5 + kw];
+#pragma unroll
+            for (int i = 0; i < 4; i++) fma4(u[i], cell[kh + kw][kh + i], w4);
+        }
+    }
+}
+
+// tc: the LARGER output group of the warp's pair (more old tap rows); the other half-warp's extra rows and channels carry zero weights
+template <int BW, int CHS>
+__device__ __forceinline__ void dc_stage_fma4(const float* bw0, const float4* wsm, int nc, int chan0, int cin_g, int tc, float4 (&u)[4]) {
+    for (int ch = 0; ch < nc; ch++) {
+        const float* bw = bw0 + ch * CHS;
+        const float4* wrow = wsm + ch * TAPS;
+        const int bound = tc + 3 - (chan0 + ch) / cin_g;  // warp-uniform
+        if (bound >= 9) { dc_taps_fma4<BW, 9>(bw, wrow, u); continue; }
+        switch (bound) {
+            case 8: dc_taps_fma4<BW, 8>(bw, wrow, u); break;
+            case 7: dc_taps_fma4<BW, 7>(bw, wrow, u); break;
+            case 6: dc_taps_fma4<BW, 6>(bw, wrow, u); break;
+            case 5: dc_taps_fma4<BW, 5>(bw, wrow, u); break;
+            case 4: dc_taps_fma4<BW, 4>(bw, wrow, u); break;
+            case 3: dc_taps_fma4<BW, 3>(bw, wrow, u); break;
+            case 2: dc_taps_fma4<BW, 2>(bw, wrow, u); break;
+            case 1: dc_taps_fma4<BW, 1>(bw, wrow, u); break;
+            default: break;
+        }
+    }
+}
+
 // previous- (gsel0 = tc + 3) or same-wavefront (gsel0 = tc + 4) taps of one 4-channel chunk: canonical order (kh, kw, c)
 template <int RS, int CS, int CHS>
 __device__ __forceinline__ void dc_stage_q(const float* band, const float4* wsm, int nc, int lane, int gsel0, int G, float4& u) {

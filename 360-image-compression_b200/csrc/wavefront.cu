@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old_kernel(const __grid_
     float4* wsm = reinterpret_cast<float4*>(band + WF_STAGE * WF_BAND);
     const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
     const unsigned wsm_s = band_s + WF_BAND_BYTES;
-    const int h0 = (t.hbase - 2) & ~3;   // aligned box start (also for negative values: two's complement floor)
-    const float* bandl = band + (t.hbase - 2 - h0);
+    const int h0 = (t.hbase - 2 + WF_HSHIFT) & ~3;   // aligned box start, in frame columns (row h = column h + WF_HSHIFT)
+    const float* bandl = band + (t.hbase - 2 + WF_HSHIFT - h0);
     const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + seg);
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old2_kernel(const __grid
     float4* wsm = reinterpret_cast<float4*>(band + WF2_STAGE * WF2_BAND);
     const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
     const unsigned wsm_s = band_s + WF2_BAND_BYTES;
-    const int h0 = (hb - 2) & ~3;          // aligned box start (also for negative values: two's complement floor)
-    const float* bandl = band + (hb - 2 - h0);   // 0 or 2 floats in
+    const int h0 = (hb - 2 + WF_HSHIFT) & ~3;          // aligned box start, in frame columns (row h = column h + WF_HSHIFT)
+    const float* bandl = band + (hb - 2 + WF_HSHIFT - h0);   // 0 or 2 floats in
     const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + seg);
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -263,6 +263,118 @@ __global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old2_kernel(const __grid
                 P.x = P.x + v.x; P.y = P.y + v.y; P.z = P.z + v.z; P.w = P.w + v.w;
             }
             L.pbuf[psum & 1][(((size_t)n * L.cpg4 + kc) * net.D + d) * net.HS + h] = P;
+        }
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(net.G, psum - dp, WF_TR_OLD1);
+}
+
+// ------------------------------------------------------------------------------------------------ old terms, 4 positions / lane
+// The old-term kernels are bound by shared-memory load wavefronts, and the two-position form spends 50 of its 88 per channel on the 25
+// weight vectors.  Here a warp takes TWO neighbouring diagonals of the slab -- output groups tc and tc - 1 -- 64 positions each:
+// 16 lanes per diagonal, four adjacent positions per lane (dc_taps_fma4).  Both diagonals read the SAME input channels around the same
+// rows, one diagonal apart: one TMA box {72 h, 10 d, 2 c} serves both (the second half-warp's band rows are one further down), and
+// each half-warp reads its own group's weight vector with a single LDS.128 (two addresses per instruction cost what a broadcast
+// costs).  114 wavefronts per channel for 400 packed FMAs instead of 88 for 200.  The lower group has fewer old terms: its missing
+// tap rows and its missing last input group are zero in the packed weights (x * 0 added to an accumulator changes nothing), and its
+// block sums beyond its own count are left out of the canonical sum like everywhere else.  Needs one output chunk per group.
+constexpr int WF4_STAGE = 2;
+constexpr int WF4_BOX_W = 72;
+constexpr int WF4_ROWS = 10;
+constexpr int WF4_BAND = WF4_ROWS * WF4_BOX_W;
+constexpr int WF4_BAND_BYTES = WF4_STAGE * WF4_BAND * 4;
+constexpr int WF4_W_BYTES = WF4_STAGE * TAPS * 16;  // weight vectors of one half-warp's group
+constexpr int WF4_STAGE_BYTES = ((WF4_BAND_BYTES + 2 * WF4_W_BYTES + 127) / 128) * 128;
+
+__global__ void __launch_bounds__(32 * WF_OLD_WARPS) wf_old4_kernel(const __grid_constant__ WfNetDev net,
+                                                                   const __grid_constant__ WfMaps maps, int dp, int l0, int parts4, int psum_x,
+                                                                   const int* __restrict__ scat_done) {
+    extern __shared__ unsigned char wf_raw[];
+    // grid = ((layer, net), 1, (diagonal pair, part)), x fastest: the heaviest output groups of every layer start first
+    const int bx = blockIdx.z, bz = blockIdx.x;
+    const int l = l0 + bz / net.nsets, n = bz % net.nsets;
+    const int psum = psum_x >= 0 ? psum_x : *net.ctr + dp;
+    if (psum >= net.nsteps) return;
+    const int la = max(0, psum - net.G + 1), lb = min(psum, net.H + net.W - 2);
+    const int dA = la + 2 * (bx / parts4);  // half-warp 0: diagonal dA, group tcA; half-warp 1: diagonal dA + 1, group tcA - 1
+    if (dA > lb) return;
+    const bool hasB = dA + 1 <= lb;
+    const int hminA = max(0, dA - net.W + 1), hmaxA = min(net.H - 1, dA);
+    const int hminB = max(0, dA + 1 - net.W + 1), hmaxB = hasB ? min(net.H - 1, dA + 1) : -1;
+    const int hb = (hminA & ~3) + (bx % parts4) * 64;  // a multiple of 4: the lane's four cells are one aligned float4 per band row
+    if (hb > max(hmaxA, hmaxB)) return;                // CTA-uniform
+    const int tcA = psum - dA;
+    if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MIN(net.G, psum - dp, WF_TR_OLD0);
+    if (scat_done && l == 0) {  // persistent decode: see wf_old2_kernel
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            unsigned long long t0 = 0, t1 = 0;
+            for (unsigned spins = 1; reinterpret_cast<const volatile int*>(scat_done)[n] < psum - 1; spins++)
+                if ((spins & 0xFFF) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t0 == 0) t0 = t1;
+                    else if (t1 - t0 > 5000000000ull) break;
+                }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const WfLayerDev& L = net.L[l];
+    const unsigned raw_s = (unsigned)__cvta_generic_to_shared(wf_raw);
+    unsigned char* base = wf_raw + ((128u - (raw_s & 127u)) & 127u);                            // 128-B aligned
+    float4* part = reinterpret_cast<float4*>(base + (size_t)WF_OLD_WARPS * WF4_STAGE_BYTES);   // [nblk][2 diagonals][64]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + L.nblk * 128);     // [WF_OLD_WARPS]
+    const int lane = threadIdx.x, seg = threadIdx.y, half = lane >> 4, l16 = lane & 15;
+    float* band = reinterpret_cast<float*>(base + (size_t)seg * WF4_STAGE_BYTES);
+    float4* wsm = reinterpret_cast<float4*>(band + WF4_STAGE * WF4_BAND);                      // [half][channel][tap]
+    const unsigned band_s = (unsigned)__cvta_generic_to_shared(band);
+    const unsigned wsm_s = band_s + WF4_BAND_BYTES;
+    // frame column of row hb - 2 is hb - 2 + WF_HSHIFT = hb: the box starts there; band row r + half <-> tap row r of this half's diagonal
+    const float* bw0 = band + half * WF4_BOX_W + 4 * l16;
+    const float4* wsm_h = wsm + half * (WF4_STAGE * TAPS);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + seg);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int Cin = L.Cin;
+    const int limA = min(Cin, (tcA + 3) * L.cin_g);              // old terms: g_in <= tc + 2
+    const int limB = hasB ? min(Cin, (tcA + 2) * L.cin_g) : 0;
+    const int nactA = (limA + CB - 1) / CB, nactB = (limB + CB - 1) / CB;  // canonical blocks that have old terms
+    unsigned phase = 0;
+    for (int j = seg; j < nactA; j += WF_OLD_WARPS) {
+        float4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int cb = min(CB, Cin - j * CB);
+        const float4* wpA = reinterpret_cast<const float4*>(L.wp) + (((size_t)n * L.nchunk + tcA) * Cin + j * CB) * TAPS;
+        const float4* wpB = wpA - (size_t)Cin * TAPS;  // group tcA - 1
+        for (int c0 = 0; c0 < cb && j * CB + c0 < limA; c0 += WF4_STAGE) {
+            const int nc = min(WF4_STAGE, cb - c0);
+            __syncwarp();  // every lane is done with the previous stage
+            if (lane == 0) {
+                mbar_expect_tx(bar, WF4_BAND_BYTES + (hasB ? 2 : 1) * nc * TAPS * 16);
+                tma_load_3d(band_s, &maps.tm[l], hb, dA - 4, n * Cin + j * CB + c0, bar);
+                bulk_load(wsm_s, wpA + c0 * TAPS, nc * TAPS * 16, bar);
+                if (hasB) bulk_load(wsm_s + WF4_W_BYTES, wpB + c0 * TAPS, nc * TAPS * 16, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            dc_stage_fma4<WF4_BOX_W, WF4_BAND>(bw0, wsm_h, nc, j * CB + c0, L.cin_g, tcA, u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) part[j * 128 + half * 64 + 4 * l16 + i] = u[i];
+    }
+    __syncthreads();
+    {   // the block sums in canonical order: one thread per output position (warps 0, 1: diagonal dA; warps 2, 3: diagonal dA + 1)
+        const int t = seg * 32 + lane, ho = t >> 6, pos = t & 63, h = hb + pos;
+        const int nact = ho ? nactB : nactA, hmin = ho ? hminB : hminA, hmax = ho ? hmaxB : hmaxA;
+        if (t < 128 && h >= hmin && h <= hmax) {
+            float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < nact; j++) {  // blocks without old terms add nothing (the encoder skips them too)
+                const float4 v = part[j * 128 + ho * 64 + pos];
+                P.x = P.x + v.x; P.y = P.y + v.y; P.z = P.z + v.z; P.w = P.w + v.w;
+            }
+            L.pbuf[psum & 1][((size_t)n * net.D + dA + ho) * net.HS + h] = P;
         }
     }
     if (threadIdx.x == 0 && threadIdx.y == 0) WF_TRACE_MAX(net.G, psum - dp, WF_TR_OLD1);
@@ -784,13 +896,42 @@ __device__ __noinline__ void wf_chain4_rows(const WfNetDev& net, const WfRows& r
 // them (wf_prev_kernel) was observed to start only when the concurrently running old-term kernel drained (+30 us on the step).
 // One item = (layer, slab position of step p + 1); arithmetic = one canonical block of 4 channels, taps in (kh, kw, c) order,
 // every tap read unconditionally from the group-padded frame (out-of-range groups are zeros times zero weights).
+// One item = (layer, PAIR of adjacent positions of one diagonal of the next slab): the two positions share their output group, so
+// every shared-memory weight vector feeds 8 FMAs, and 16 of their 2 x 25 taps (tap (kh, kw) of the upper position is tap
+// (kh + 1, kw - 1) of the lower one).  Pairs are formed inside each diagonal's segment of the CTA's chunk, from the segment start; a
+// segment of odd length ends in a single.  The item loop is bound by shared-memory wavefronts like the old-term kernels.
+struct WfPairPos { int d, h, single; };
+
+// pair q of the chunk [k0, k0 + nloc) of the plan (diagonal-major, rows ascending); q < 0: returns the number of pairs in .h
+__device__ __forceinline__ WfPairPos wf_tail_pair(const WfNetDev& net, int k0, int nloc, int q) {
+    const int HW = net.H * net.W;
+    const int hf = __ldg(net.idx + k0);
+    int d = hf + __ldg(net.idx + k0 + HW);
+    int a = hf - max(0, d - net.W + 1);  // offset of the chunk's first position inside its diagonal
+    int left = nloc, total = 0;
+    WfPairPos r = {0, 0, 0};
+    while (left > 0) {
+        const int hmin = max(0, d - net.W + 1), dlen = min(net.H - 1, d) - hmin + 1;
+        const int seg = min(dlen - a, left), np = (seg + 1) >> 1;
+        if (q >= 0 && q < np) {
+            r.d = d; r.h = hmin + a + 2 * q; r.single = 2 * q + 1 >= seg;
+            return r;
+        }
+        q -= np; total += np; left -= seg; d++; a = 0;
+    }
+    r.h = total;
+    return r;
+}
+
 __device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int psum1, int tid, int nt, const WfTailPlan& tail) {
     extern __shared__ float4 wf_wsm[];
     if (psum1 >= net.nsteps || tail.nloc == 0) return;  // uniform per CTA
     if (tid == 0) WF_TRACE_MIN(net.G, psum1 - 1, WF_TR_TAIL0);
     const StepDesc s1 = net.steps[psum1];
-    const int HW = net.H * net.W, GP = net.G + 2 * WF_GPAD;
+    const int GP = net.G + 2 * WF_GPAD;
     const size_t srow = (size_t)(GP - 1) * net.Hp;
+    const int k0 = s1.start + tail.i0;
+    const int npairs = wf_tail_pair(net, k0, tail.nloc, -1).h;
     for (int l0 = 1; l0 < WF_LAYERS; l0 += tail.lpg) {
         const int nl = min(tail.lpg, WF_LAYERS - l0);
         if (l0 > 1) {  // (the first group was staged in wf_chain4_rows)
@@ -799,33 +940,43 @@ __device__ __noinline__ void wf_chain4_rtail(const WfNetDev& net, int n, int psu
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
-        for (int it = tid; it < nl * tail.nloc; it += nt) {
-            const int lr = it / tail.nloc, il = it - lr * tail.nloc;
+        for (int it = tid; it < nl * npairs; it += nt) {
+            const int lr = it / npairs;
+            const WfPairPos pp = wf_tail_pair(net, k0, tail.nloc, it - lr * npairs);
             const WfLayerDev& L = net.L[l0 + lr];
-            const int k = s1.start + tail.i0 + il;
-            const int h = __ldg(net.idx + k), d = h + __ldg(net.idx + k + HW), tc = psum1 - d;
-            // tap (kh, kw), s = kh + kw, selects group tc + 3 - s: cell = xr + s * srow + kh, float4 units
+            const int h = pp.h, d = pp.d, tc = psum1 - d;
+            // tap (kh, kw), s = kh + kw, selects group tc + 3 - s: cell = xr + s * srow + kh (+ 1 for the upper position), float4 units
             const float4* xr = reinterpret_cast<const float4*>(L.xc) + (((size_t)n * net.Dp + d) * GP + WF_GPAD + tc + 3) * net.Hp + h;
             const float4* wr = wf_wsm + ((size_t)lr * tail.nrows + (tc - tail.tc_lo)) * WF_ROW_F4;
-            float4 xv[TAPS];
+            float4 cell[9][6];
 #pragma unroll
-            for (int kh = 0; kh < 5; kh++)
+            for (int sd = 0; sd < 9; sd++) {
+                const int khmin = sd > 4 ? sd - 4 : 0, khmax = sd < 4 ? sd : 4;
 #pragma unroll
-                for (int kw = 0; kw < 5; kw++) xv[kh * 5 + kw] = WF_TAP_LOAD(xr + (kh + kw) * srow + kh);  // this cluster's stores, behind its barriers
-            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int col = 0; col < 6; col++) {
+                    if (col < khmin || col > khmax + 1) continue;
+                    // this cluster's stores, behind its barriers; a single's upper cells would leave the diagonal: not read
+                    if (col == khmax + 1 && pp.single) cell[sd][col] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    else cell[sd][col] = WF_TAP_LOAD(xr + sd * srow + col);
+                }
+            }
+            float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
 #pragma unroll
             for (int kh = 0; kh < 5; kh++)
 #pragma unroll
                 for (int kw = 0; kw < 5; kw++) {
-                    const float4 x4 = xv[kh * 5 + kw];
-                    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                    const float4 a4 = cell[kh + kw][kh], b4 = cell[kh + kw][kh + 1];
+                    const float as[4] = {a4.x, a4.y, a4.z, a4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         const float4 w4 = wr[(kh * 5 + kw) * 4 + c];
-                        fma4(u, xs[c], w4);
+                        fma4(u0, as[c], w4);
+                        fma4(u1, bs[c], w4);
                     }
                 }
-            L.rbuf[psum1 & 1][((size_t)n * net.D + d) * net.HS + h] = make_float4(0.f + u.x, 0.f + u.y, 0.f + u.z, 0.f + u.w);  // R = 0 + r_0
+            float4* dst = L.rbuf[psum1 & 1] + ((size_t)n * net.D + d) * net.HS + h;
+            dst[0] = make_float4(0.f + u0.x, 0.f + u0.y, 0.f + u0.z, 0.f + u0.w);  // R = 0 + r_0
+            if (!pp.single) dst[1] = make_float4(0.f + u1.x, 0.f + u1.y, 0.f + u1.z, 0.f + u1.w);
         }
     }
     __syncthreads();  // the next step's (or launch's) layer loop stages into these buffers again
@@ -1379,7 +1530,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     WfNetDev& n = e.dev;
     memset(&n, 0, sizeof(n));
     n.nsets = nsets; n.G = G; n.H = H; n.W = W; n.Dp = H + W - 1 + 8; n.Hp = H + 4;
-    n.D = H + W - 1; n.HS = (H + 3) & ~3;
+    n.D = H + W - 1; n.HS = (H + WF_HSHIFT + 3) & ~3;
     n.nsteps = nsteps; n.parts = (std::min(H, W) + 31) / 32; n.ndiag = std::min(G, n.D);
     n.steps = steps_dev; n.ctr = ctr_dev; n.idx = idx_dev;
     e.max_len = max_len;
@@ -1432,6 +1583,11 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled (72-wide box) failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
+        const cuuint32_t box4[3] = {WF4_BOX_W, WF4_ROWS, WF4_STAGE};
+        r = enc(&e.maps4.tm[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, e.fp[l], dims, strides, box4, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wavefront engine: cuTensorMapEncodeTiled (10-row box) failed (%d) for layer %d", (int)r, l); return LIC360_ERR_CUDA; }
     }
     // launch shapes
     e.old_smem = 128 + (size_t)WF_OLD_WARPS * WF_STAGE_BYTES + (size_t)e.nblk_max * 32 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
@@ -1442,16 +1598,25 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     // a diagonal with an odd first row starts its tile one position early; only when H > W can such a diagonal have full length
     e.parts2 = (std::min(H, W) + (H > W ? 1 : 0) + 63) / 64;
     e.old2_smem = 128 + (size_t)WF_OLD_WARPS * WF2_STAGE_BYTES + (size_t)e.nblk_max * 64 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
+    // four positions per lane, two diagonals per warp: nets with one output chunk per group (LIC360_WF_OLD2=1: the two-position kernel)
+    e.old4 = e.old2 && e.cpg4_max == 1 && getenv("LIC360_WF_OLD2") == nullptr;
+    e.parts4 = 1;
+    for (int d = 0; d < n.D; d++) {  // a diagonal's tile starts at the multiple of 4 below its first row
+        const int hmin = std::max(0, d - W + 1), hmax = std::min(H - 1, d);
+        e.parts4 = std::max(e.parts4, (hmax - (hmin & ~3) + 64) / 64);
+    }
+    e.old4_smem = 128 + (size_t)WF_OLD_WARPS * WF4_STAGE_BYTES + (size_t)e.nblk_max * 128 * sizeof(float4) + (size_t)WF_OLD_WARPS * 8;
     e.prev_wcap = 0;
     for (int l = 0; l < WF_LAYERS; l++) e.prev_wcap = std::max(e.prev_wcap, TAPS * n.L[l].cin_g);
     e.prev_smem = ((size_t)e.prev_wcap + (size_t)e.nqb_max * 32) * sizeof(float4);
     // the attribute is per kernel AND per device, not per engine: only ever raise it (two engines with different channel counts
     // share it), and remember it for every device separately (SmemAttr, common.cuh)
-    static SmemAttr prev_attr_a, prev_attr_b, old_attr, old2_attr, chain_attr_g, chain_attr_4, chain_attr_1;
+    static SmemAttr prev_attr_a, prev_attr_b, old_attr, old2_attr, old4_attr, chain_attr_g, chain_attr_4, chain_attr_1;
     LIC360_CUDA(prev_attr_a.ensure(wf_prev_kernel<320>, e.prev_smem));
     LIC360_CUDA(prev_attr_b.ensure(wf_prev_kernel<1024>, e.prev_smem));
     LIC360_CUDA(old_attr.ensure(wf_old_kernel, e.old_smem));
     LIC360_CUDA(old2_attr.ensure(wf_old2_kernel, e.old2_smem));
+    LIC360_CUDA(old4_attr.ensure(wf_old4_kernel, e.old4_smem));
     // chain kernels: one cluster per net.  16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
     // else the portable maximum of 8.
     LIC360_CUDA(cudaFuncSetAttribute(wf_chain_kernel<384>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1569,7 +1734,7 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(32, WF_OLD_WARPS);
-    cfg.dynamicSmemBytes = e.old2 ? e.old2_smem : e.old_smem;
+    cfg.dynamicSmemBytes = e.old4 ? e.old4_smem : e.old2 ? e.old2_smem : e.old_smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start once the previous kernel's CTAs have all
@@ -1581,12 +1746,14 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     const int split = n.G > 1 ? split_env : 1;
     for (int k = 0; k < split; k++) {
         const int l0 = k * WF_LAYERS / split, l1 = (k + 1) * WF_LAYERS / split;
-        cfg.gridDim = dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * (e.old2 ? e.parts2 : n.parts));
+        cfg.gridDim = e.old4 ? dim3((l1 - l0) * n.nsets, 1, ((n.ndiag + 1) / 2) * e.parts4)
+                             : dim3((l1 - l0) * n.nsets, e.cpg4_max, n.ndiag * (e.old2 ? e.parts2 : n.parts));
         cfg.numAttrs = programmatic && k == 0 ? 1 : 0;
         g_launches++;
         if (psum >= 0 && !e.old2) return cudaErrorInvalidValue;  // explicit steps: many-group engines only
-        const cudaError_t err = e.old2 ? cudaLaunchKernelEx(&cfg, wf_old2_kernel, n, e.maps2, dp, l0, e.parts2, psum, scat_done)
-                                       : cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
+        const cudaError_t err = e.old4   ? cudaLaunchKernelEx(&cfg, wf_old4_kernel, n, e.maps4, dp, l0, e.parts4, psum, scat_done)
+                                : e.old2 ? cudaLaunchKernelEx(&cfg, wf_old2_kernel, n, e.maps2, dp, l0, e.parts2, psum, scat_done)
+                                         : cudaLaunchKernelEx(&cfg, wf_old_kernel, n, e.maps, dp, l0);
         if (err != cudaSuccess) return err;
     }
     if (done) {

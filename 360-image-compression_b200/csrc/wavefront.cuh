@@ -78,6 +78,10 @@ struct WfEngine {
     bool old2 = false;    // use it (many-group nets; LIC360_WF_OLD1=1 switches back)
     int parts2 = 1;       // 64-position parts per diagonal
     size_t old2_smem = 0;
+    WfMaps maps4;         // box {72 h, 10 d, 2 c} of the four-positions-per-lane, two-diagonals-per-warp old-term kernel
+    bool old4 = false;    // use it (many-group nets with one output chunk per group; LIC360_WF_OLD2=1 switches back)
+    int parts4 = 1;
+    size_t old4_smem = 0;
     float* fp[WF_LAYERS + 1] = {nullptr};
     float* fc[WF_LAYERS + 1] = {nullptr};
     size_t fp_floats[WF_LAYERS + 1] = {0}, fc_floats[WF_LAYERS + 1] = {0};
@@ -142,8 +146,13 @@ void wf_trace_set(unsigned long long* buf, int sel);  // sel: 0 = trace the mult
         }                                                                                                 \
     } while (0)
 
+// Planar skewed frame: row h of diagonal d lives in column h + WF_HSHIFT.  A 5x5 window starts two rows above its position, and the
+// TMA unit wants box starts that are multiples of 4 floats: with the shift the box of a tile starting at row hb (a multiple of 4) starts
+// at column hb, and a lane's first cell is 16-byte aligned in shared memory (wf_old4_kernel reads the band as float4).  Columns 0, 1
+// and everything right of the image are never written: zeros (or the TMA unit's out-of-bounds fill).
+constexpr int WF_HSHIFT = 2;
 __host__ __device__ inline size_t wf_fp_index(int D, int HS, int C, int n, int c, int d, int h) {
-    return (((size_t)n * C + c) * D + d) * HS + h;
+    return (((size_t)n * C + c) * D + d) * HS + h + WF_HSHIFT;
 }
 
 }  // namespace lic360
