@@ -11,7 +11,7 @@ dev = "cuda:0"
 H, W = int(sys.argv[1]), int(sys.argv[2])
 q, mask, lv = synthetic_latent(77, H=H, W=W)
 params = pl.make_codec_params(dev)
-fused = pl.FusedCodec(params, H=H, W=W)
+fused = pl.FusedCodec(params, H=H, W=W, mode=int(os.environ.get("LIC360_MODE", "0")))
 tq, tm, tl = t(q, dev), t(mask, dev), t(lv, dev)
 for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 2):
     t0 = time.time(); bi, bc = fused.encode(tq, tm, tl); t1 = time.time()
