@@ -564,7 +564,7 @@ static int build_step_graph(lic360_codec* c, NetDesc& n, bool is_code) {
     cudaGraph_t g;
     const long long l0 = g_launches;
     LIC360_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    static const bool overlap = getenv("LIC360_WF_NO_OVERLAP") == nullptr;
+    const bool overlap = getenv("LIC360_WF_NO_OVERLAP") == nullptr;  // (graph build time: not on a hot path)
     const int rc = launch_step(c, n, is_code, s, overlap ? n.side : s, nullptr);
     cudaError_t e = cudaStreamEndCapture(s, &g);
     n.graph_nodes = (int)(g_launches - l0);

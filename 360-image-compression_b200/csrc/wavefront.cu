@@ -1742,7 +1742,7 @@ cudaError_t wf_launch_old(const WfEngine& e, int dp, cudaStream_t s, bool progra
     cfg.attrs = attr;
     // LIC360_WF_OLD_SPLIT=k (experiment): k launches over layer ranges, so that the grid drains k times per step and a
     // cluster launch of the other bitstream's chain, which needs whole SMs, gets a window
-    static const int split_env = getenv("LIC360_WF_OLD_SPLIT") ? std::max(1, std::min(WF_LAYERS, atoi(getenv("LIC360_WF_OLD_SPLIT")))) : 1;
+    const int split_env = getenv("LIC360_WF_OLD_SPLIT") ? std::max(1, std::min(WF_LAYERS, atoi(getenv("LIC360_WF_OLD_SPLIT")))) : 1;
     const int split = n.G > 1 ? split_env : 1;
     for (int k = 0; k < split; k++) {
         const int l0 = k * WF_LAYERS / split, l1 = (k + 1) * WF_LAYERS / split;

@@ -279,3 +279,25 @@ def test_fused_codec_low_latency_mode_two_decodes_at_once():
     for x in th:
         x.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("switch", ["LIC360_WF_OLD1", "LIC360_WF_OLD2", "LIC360_WF_ROWS_KERNEL", "LIC360_WF_PREV_KERNEL", "LIC360_WF_R0_KERNEL",
+                                    "LIC360_WF_ROWS_FLAGS", "LIC360_WF_SHARE_SM", "LIC360_WF_NO_OVERLAP", "LIC360_WF_OLD_SPLIT=3",
+                                    "LIC360_WF_LAUNCH_AHEAD", "LIC360_EC_RQ_GENERIC"])
+def test_fused_codec_alternate_kernel_paths(monkeypatch, switch):
+    """Every kernel the default pipeline replaced is still selectable by an environment switch and is the reference
+    point of an A/B number in DESIGN.md: each must still produce the same bytes and the same symbols as the default path."""
+    import lic360_pipeline as pl
+    H, W = 24, 72  # diagonals of up to 24 positions, 142 code-stream steps
+    q, mask, lv = synthetic_latent(71, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=71)
+    tq, tm, tl = t(q, DEV), t(mask, DEV), t(lv, DEV)
+    default = pl.FusedCodec(params, H=H, W=W)
+    bi, bc = default.encode(tq, tm, tl)
+    name, _, value = switch.partition("=")
+    monkeypatch.setenv(name, value or "1")
+    alt = pl.FusedCodec(params, H=H, W=W)
+    assert alt.encode(tq, tm, tl) == (bi, bc)
+    for _ in range(2):
+        code, mup = alt.decode(bi, bc)
+        assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
