@@ -1626,6 +1626,7 @@ int wf_init(WfEngine& e, int G, int cpg, int nlast, int nsets, int H, int W, con
     // has one cluster and splits output chunks: 16
     int want = G > 1 ? 8 : 16;
     if (const char* s = getenv("LIC360_WF_CLUSTER")) want = std::max(1, std::min(16, atoi(s)));
+    if (const char* s = getenv(G > 1 ? "LIC360_WF_CLUSTER_CODE" : "LIC360_WF_CLUSTER_IMP")) want = std::max(1, std::min(16, atoi(s)));
     for (e.cluster = want;; e.cluster = 8) {
         int tasks_max = 0;
         for (int l = 0; l < WF_LAYERS; l++) {
