@@ -373,6 +373,35 @@ def main():
     except Exception as e:  # secondary figure only
         cfg3 = {"unavailable": repr(e)}
 
+    # ---- configs[3]: ONE 2048x4096 image (latent 256x512), decode stress.  Inside an image the wavefront and the arithmetic-coded
+    # stream are sequential, so the reference's format does not shard (single stream: one GPU); the latitude-band
+    # FORMAT EXTENSION does (lic360_shard.BandCodec: 8 independently coded bands of 32 latent rows, dealt round-robin to the ranks).
+    cfg4 = None
+    try:
+        if os.environ.get("LIC360_BENCH_NO_CONFIG4"):
+            raise RuntimeError("disabled by LIC360_BENCH_NO_CONFIG4")
+        H4, W4, NB4 = 256, 512, 8
+        a4, b4, c4 = [torch.from_numpy(v).to(dev) for v in synthetic_latent(4000, H4, W4)]  # the same image on every rank
+        bands = sh.BandCodec(lambda h, w: pl.FusedCodec(params, H=h, W=w, gid=local_rank), H4, W4, NB4, world=world, rank=rank,
+                             in_flight=4 if world == 1 else 2)
+        blob4 = bands.encode(a4, b4, c4)
+        bands.decode_local(blob4)  # warm-up
+        barrier()
+        t0 = time.time()
+        local4 = bands.decode_local(blob4)
+        torch.cuda.synchronize()
+        ms4 = sh.max_over_ranks((time.time() - t0) * 1e3, dev)
+        ok4 = all(bool(torch.equal(cb, (a4 * b4)[:, :, r0:r1])) and bool(torch.equal(mb, b4[:, :, r0:r1]))
+                  for bnd, (cb, mb) in local4.items() for r0, r1 in [bands.rows[bnd]])
+        cfg4 = {"value": (2048 * 4096 / 1e6) / (ms4 / 1e3), "unit": "Mpx/s (decode only)", "image": [2048, 4096], "latent": [1, 48, H4, W4],
+                "bands": NB4, "bands_per_gpu": len(bands.mine), "in_flight_per_gpu": len(bands.codecs), "decode_ms": ms4,
+                "container_bytes": len(blob4), "round_trip_exact": ok4, "timing": "host wall clock around this rank's bands, max over ranks",
+                "note": "configs[3]: one 2048x4096 image as 8 independently coded latitude bands (format extension: per band the bytes are what "
+                        "the codec emits for the band as an image of its own); the single-stream decode of the same image takes 218 ms on one GPU"}
+        del bands, local4
+    except Exception as e:  # secondary figure only
+        cfg4 = {"unavailable": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -452,6 +481,7 @@ def main():
                                         "round_trip_exact": piped_ok, "timing": "host wall clock around all worker threads, max over ranks",
                                         "note": "secondary figure; `value` and `e2e` are one image at a time"}
     line["config3_1024x2048_batch16"] = cfg3
+    line["config4_2048x4096_bands"] = cfg4
     if sampler:
         line["clocks"] = sampler.summary()
     if world == 1 and not args.no_cpu_baseline:

@@ -301,3 +301,28 @@ def test_fused_codec_alternate_kernel_paths(monkeypatch, switch):
     for _ in range(2):
         code, mup = alt.decode(bi, bc)
         assert np.array_equal(n(code), q * mask) and np.array_equal(n(mup), mask)
+
+
+def test_band_codec_round_trip():
+    """One image as independently coded latitude bands (lic360_shard.BandCodec: BASELINE.json configs[3], a format extension -- SURVEY.md
+    s8e option 3): every band's two streams are exactly the bytes the codec emits for that band as an image of its own, the container
+    decodes to the image, and the price of the lost context at the band edges stays small."""
+    import lic360_pipeline as pl
+    import lic360_shard as sh
+    H, W, NB = 64, 128, 4
+    q, mask, lv = synthetic_latent(81, H=H, W=W)
+    params = pl.make_codec_params(DEV, seed=81)
+    tq, tm, tl = t(q, DEV), t(mask, DEV), t(lv, DEV)
+    bc = sh.BandCodec(lambda h, w: pl.FusedCodec(params, H=h, W=w), H, W, NB, in_flight=2)
+    blob = bc.encode(tq, tm, tl)
+    h, w, streams = sh.unpack_band_streams(blob)
+    assert (h, w, len(streams)) == (H, W, NB)
+    one = pl.FusedCodec(params, H=H // NB, W=W)
+    for b, (r0, r1) in enumerate(sh.band_rows(H, NB)):
+        alone = one.encode(tq[:, :, r0:r1].contiguous(), tm[:, :, r0:r1].contiguous(), tl[:, :, r0 // 2:r1 // 2].contiguous())
+        assert streams[b] == alone
+    code, m = bc.decode(blob, like=tq)
+    assert np.array_equal(n(code), q * mask) and np.array_equal(n(m), mask)
+    single = pl.FusedCodec(params, H=H, W=W).encode(tq, tm, tl)
+    total, ref = sum(len(a) + len(b) for a, b in streams), len(single[0]) + len(single[1])
+    assert 0.9 * ref <= total <= 1.1 * ref, (total, ref)
