@@ -21,7 +21,10 @@
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <cstring>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <sched.h>
 #include <thread>
 #include <cmath>
@@ -89,21 +92,25 @@ struct ChainSlots {
     std::mutex m;
     std::condition_variable cv;
     int in_use[kMaxDevices] = {0};
-    void acquire(int dev, int cap) {
+    void acquire(int dev, int cap, int units) {
         std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [&] { return in_use[dev] < cap; });
-        in_use[dev]++;
+        cv.wait(lk, [&] { return in_use[dev] + units <= cap; });
+        in_use[dev] += units;
     }
-    void release(int dev) {
-        { std::lock_guard<std::mutex> lk(m); in_use[dev]--; }
+    void release(int dev, int units) {
+        { std::lock_guard<std::mutex> lk(m); in_use[dev] -= units; }
         cv.notify_all();
     }
 };
 static ChainSlots g_chain_slots;
+// units = 1: a graph-replay decode; units = cap: a low-latency decode, which owns the device while it runs -- its chain clusters stay
+// resident from the first to the last step, and with several of them pinned (24 SMs each, wherever the hardware found room) the
+// 16-CTA cluster of an importance stream may not find a GPC with enough free SMs for as long as they run (observed: decodes timing
+// out waiting for importance levels with two or more resident chains and decodes starting and finishing around them)
 struct ChainSlot {
-    int dev;
-    ChainSlot(int d, int cap) : dev(d) { g_chain_slots.acquire(d, cap); }
-    ~ChainSlot() { g_chain_slots.release(dev); }
+    int dev, units;
+    ChainSlot(int d, int cap, int u) : dev(d), units(std::max(1, std::min(u, cap))) { g_chain_slots.acquire(d, cap, units); }
+    ~ChainSlot() { g_chain_slots.release(dev, units); }
 };
 
 // the importance stream of a decode runs on a second host thread: one persistent worker per codec (not a std::thread per call)
@@ -1119,6 +1126,12 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         wf_trace_set(trace_dev, tr_sel);
         codec_trace_set(trace_dev, tr_sel);
     }
+    // Admission first: a decode queues here when the device already runs as many decodes as it can hold, and a low-latency decode takes
+    // the device for itself.  Everything below -- graph capture and instantiation included, which may allocate and therefore wait for the
+    // device -- runs inside the slot: a thread that blocks in the driver while ANOTHER decode's persistent kernel waits for its host
+    // would stall that decode's importance-stream launches (observed as a 20 s "levels" time-out under a 7-thread stress).
+    std::unique_ptr<ChainSlot> slot;
+    if (c->mode != 1) slot.reset(new ChainSlot(c->device, c->chain_cap, persistent_ok(c, c->code) ? c->chain_cap : 1));
     if (c->mode != 1) {  // both step graphs exist before the second host thread starts (the persistent code stream needs none)
         rc = build_step_graph(c, c->imp, false);
         if (rc == LIC360_OK && !persistent_ok(c, c->code)) rc = build_step_graph(c, c->code, true);
@@ -1140,11 +1153,17 @@ int lic360_codec_decode(lic360_codec* c, const uint8_t* imp_bytes, long n_imp, c
         c->t_imp = ms_since(t0);
     };
     if (c->mode != 1) {
-        ChainSlot slot(c->device, c->chain_cap);  // queues here when the device already runs as many decodes as it can hold
         c->imp_worker.submit(imp_loop);
         rc = decode_stream(c, c->code, true);
-        if (rc) c->abort_flag.store(1);
+        std::string code_err;
+        if (rc) { code_err = lic360_last_error(); c->abort_flag.store(1); }
         c->imp_worker.wait();
+        // both failed: the stream that failed FIRST carries the cause, the other one only reports the abort it was told about
+        if (rc && rc_imp && strstr(c->imp.err, "aborted (the other stream failed)")) {
+            set_error("%s", code_err.c_str());
+            cudaStreamSynchronize(c->code.stream); cudaStreamSynchronize(c->imp.stream);
+            return rc;
+        }
     } else {
         imp_loop();
         if (rc_imp == LIC360_OK) rc = decode_stream(c, c->code, true);

@@ -233,7 +233,10 @@ int lic360_codec_last_timing(lic360_codec* c, double* out, int n);
  * mode 2 (low latency, opt-in): the code stream's chain kernel is launched ONCE per decode and walks all wavefront steps; between
  * steps it polls the symbols the host publishes in mapped memory (every symbol word carries a publication tag) instead of being
  * re-launched, so no graph launch, scatter kernel or kernel prologue sits between the host's last decoded symbol and the next
- * step.  Same bitstreams, same results.  Its three 8-CTA clusters stay resident for the whole decode (24 SMs per decode in flight). */
+ * step.  Same bitstreams, same results.  Its three 8-CTA clusters stay resident for the whole decode, so a mode-2 decode takes the device
+ * for itself: other decodes on the same GPU queue until it is done (encodes do not).  Caveat: while it runs, a call from ANOTHER host
+ * thread that makes the driver wait for the device (cudaFree, a graph instantiation, ...) can hold the driver lock the decode's own
+ * launches need; the kernel's bail-outs (20 s) then fail the decode instead of hanging.  A latency mode for one image at a time. */
 int lic360_codec_set_mode(lic360_codec* c, int mode);
 /* after a mode-1 decode: total milliseconds of the last decode spent in [0] the old-term kernel, [1] the previous-wavefront
  * kernel, [2] the 12-layer chain kernel, [3] scatter + CDF-row kernels, and [4] the number of steps, for one stream */

@@ -252,14 +252,16 @@ def test_fused_codec_low_latency_mode(H, W, seed):
     assert np.array_equal(n(code0), n(code)) and np.array_equal(n(mup0), n(mup))
 
 
-def test_fused_codec_low_latency_mode_two_decodes_at_once():
-    """Two persistent decodes on one GPU (2 x 3 resident clusters) from two host threads: both finish, both exact."""
+@pytest.mark.parametrize("ncodec", [2, 7])
+def test_fused_codec_low_latency_mode_several_decodes_at_once(ncodec):
+    """Persistent decodes on one GPU from several host threads (3 resident clusters = 24 SMs each): all finish, all exact.  Seven is more
+    than the device can keep resident next to the importance streams' clusters: the surplus decodes queue on the host (codec.cu)."""
     import threading
     import lic360_pipeline as pl
     H, W = 64, 128
     params = pl.make_codec_params(DEV, seed=61)
-    codecs = [pl.FusedCodec(params, H=H, W=W, mode=2) for _ in range(2)]
-    lat = [synthetic_latent(600 + k, H=H, W=W) for k in range(2)]
+    codecs = [pl.FusedCodec(params, H=H, W=W, mode=2) for _ in range(ncodec)]
+    lat = [synthetic_latent(600 + k, H=H, W=W) for k in range(ncodec)]
     errors = []
 
     def worker(k):
@@ -273,7 +275,7 @@ def test_fused_codec_low_latency_mode_two_decodes_at_once():
         except Exception as e:  # noqa: BLE001
             errors.append((k, repr(e)))
 
-    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(ncodec)]
     for x in th:
         x.start()
     for x in th:
